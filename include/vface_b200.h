@@ -1,0 +1,131 @@
+/*
+ * vface_b200 -- C-ABI of the B200-native VFace denoising hot path.
+ *
+ * The reference (Sanoojan/VFace, REFace/) is pure Python/PyTorch and has no FFI
+ * of its own, so every entry point below replaces a
+ * span of reference Python; the file:line each one replaces is cited.  Paths are
+ * relative to /root/reference/REFace.
+ *
+ * Conventions:
+ *   - the caller owns every buffer; nothing here allocates device memory;
+ *   - every launch is asynchronous on `stream` (a cudaStream_t passed as void*)
+ *     and is CUDA-graph capturable;
+ *   - return 0 on success, non-zero on failure with a message in
+ *     vf_last_error() (thread-local);
+ *   - there is no CPU fallback: without an sm_100a device the calls fail.
+ *   - dtype: VF_F32 is the fp32 reference-precision path, VF_BF16 the tensor-core
+ *     path (bf16 storage, fp32 accumulation).
+ *   - token tensors use the reference's native (batch, n, heads*d_head) layout;
+ *     `ld_*` are row strides in ELEMENTS (>= heads*d_head), batch stride is n*ld.
+ */
+#ifndef VFACE_B200_H_
+#define VFACE_B200_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VF_F32 0
+#define VF_BF16 1
+
+#define VF_ABI_VERSION 1
+
+/* ABI version of the loaded library (== VF_ABI_VERSION). */
+int vf_abi_version(void);
+
+/* Message of the last failing call on this thread ("" if none). */
+const char* vf_last_error(void);
+
+/*
+ * Fused attention core: o = softmax(q k^T * scale) v per (batch, head), streaming
+ * (no n_q x n_kv matrix in HBM).
+ * Replaces ldm/models/pnp_utils.py:270-286 (patched attn1) and
+ * ldm/modules/attention.py:203-220 (CrossAttention.forward core).
+ * Optional second key/value segment (k2, v2, n_kv2 rows) is treated as concatenated
+ * after (k, v) along the key axis ("injected target-frame K/V"; BASELINE.json config 3;
+ * no reference function).  Pass k2 = v2 = NULL, n_kv2 = 0 to disable.
+ * d_head must be a multiple of 8, 8 <= d_head <= 192 (bf16) / <= 256 (fp32).
+ */
+int vf_attn_fwd(const void* q, const void* k, const void* v, void* o,
+                int batch, int heads, int n_q, int n_kv, int d_head,
+                long long ld_q, long long ld_k, long long ld_v, long long ld_o,
+                float scale,
+                const void* k2, const void* v2, int n_kv2, long long ld_k2, long long ld_v2,
+                int dtype, void* stream);
+
+/*
+ * Frequency Spectrum Attention Interpolation of one (donor, dst) pair:
+ *   out[r, :] = Re ifft( [ fft(dst[r])[0:split] , fft(donor[r])[split:d] ] )
+ * along the channel axis (length d) of each of `rows` token rows.
+ * Replaces scripts/face_swap_utils.py:425-464 (combine_fft_high_low) and the slice
+ * assignment at ldm/models/pnp_utils.py:179-183 / :195-199.  `out` may alias `dst`
+ * (the reference assigns in place).  d must be 2^a * 5^b with 32 <= d <= 2048.
+ */
+int vf_fsai_blend(const void* donor, const void* dst, void* out,
+                  long long rows, int d, int split,
+                  long long ld_donor, long long ld_dst, long long ld_out,
+                  int dtype, void* stream);
+
+/*
+ * The two calls of one tensor (q or k) of a hooked module fused: both branches share the
+ * donor (chunk 0).  out_a/out_b may alias dst_a/dst_b.
+ * Replaces ldm/models/pnp_utils.py:195+:198 (q) or :196+:199 (k).
+ */
+int vf_fsai_blend2(const void* donor,
+                   const void* dst_a, void* out_a,
+                   const void* dst_b, void* out_b,
+                   long long rows, int d, int split,
+                   long long ld_donor, long long ld_a, long long ld_out_a,
+                   long long ld_b, long long ld_out_b,
+                   int dtype, void* stream);
+
+/*
+ * Flow-Guided Attention Temporal Smoothening on the native token layout
+ * x: (frames, h*w, c), row stride ld_x:
+ *   out[0]   = x[0]                                     (or blended with prev_halo, below)
+ *   out[i+1] = alpha * x[i+1] + (1-alpha) * bilinear_border_sample(x[i], p + flow[i])
+ * Replaces scripts/temporal_flow.py:222-237 (align_by_flow) + :40-53 (warp_image) and the
+ * permute/reshape round trip at ldm/models/pnp_utils.py:206-218.
+ * flow: fp32 (n_flow, 2, h, w), channel 0 = x displacement, 1 = y, feature-pixel units.
+ *   prev_halo == NULL: n_flow = frames-1, flow[i] maps frame i -> i+1.
+ *   prev_halo != NULL: (h*w, c) rows (stride ld_halo) = last frame of the previous frame
+ *     shard; n_flow = frames and flow[0] maps the halo frame -> frame 0.
+ * `out` must not alias `x`.  The source index chain is fp32 in the reference's op order
+ * (floor indices are bit-exact with torch grid_sample).  c*sizeof(elem) must be a multiple of 16.
+ * taps_out (optional, may be NULL): int32 (n_flow, h*w, 2) receives the (x0, y0) floor
+ * indices used, for index-parity tests.
+ * alpha is a double so that (1 - alpha) is formed in double like the reference's Python scalar
+ * (temporal_flow.py:234) before both weights are rounded to fp32.
+ */
+int vf_flow_warp_blend(const void* x, const void* prev_halo, const float* flow, void* out,
+                       int frames, int h, int w, int c,
+                       long long ld_x, long long ld_halo, long long ld_out,
+                       double alpha, int dtype, int* taps_out, void* stream);
+
+/*
+ * Classifier-free guidance + DDIM update, fused:
+ *   e = e_u + s (e_c - e_u); pred_x0 = (x - sqrt(1-a_t) e)/sqrt(a_t);
+ *   x_prev = sqrt(a_prev) pred_x0 + sqrt(1 - a_prev - sigma^2) e + sigma * noise
+ * Replaces ldm/models/diffusion/ddim_w_inv.py:666 and :679-700 (also :591, :604-616).
+ * x, x_prev, pred_x0, noise are fp32 (n elements each); e_uncond / e_cond have
+ * dtype `dtype_e`.  noise may be NULL when sigma_t == 0.
+ */
+int vf_ddim_cfg_step(const void* x, const void* e_uncond, const void* e_cond,
+                     void* x_prev, void* pred_x0,
+                     float a_t, float a_prev, float sigma_t, float sqrt_one_minus_at,
+                     float cfg_scale, const void* noise, long long n, int dtype_e, void* stream);
+
+/*
+ * Forward-DDIM (inversion) update of ddim_invert, fused with optional CFG:
+ *   e = e_c (e_uncond == NULL) or e_u + s (e_c - e_u)
+ *   x_next = (x - sqrt(1-a_cur) e) * sqrt(a_next)/sqrt(a_cur) + sqrt(1-a_next) e
+ * Replaces ldm/models/diffusion/ddim_w_inv.py:426-449.
+ */
+int vf_ddim_invert_step(const void* x, const void* e_uncond, const void* e_cond, void* x_next,
+                        float a_cur, float a_next, float cfg_scale,
+                        long long n, int dtype_e, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VFACE_B200_H_ */

@@ -1,0 +1,320 @@
+"""GPU parity of the four kernels, called through the C-ABI, against the numpy oracle.
+
+Tolerances (BASELINE.json north_star): per-kernel outputs within 2e-2 max-abs in bf16; fp32 paths
+are held much tighter (stated per test); flow floor indices bit-exact.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import kernels as ok
+
+pytestmark = pytest.mark.gpu
+
+BF16_TOL = 2e-2
+
+
+def _dev():
+    return torch.device("cuda:0")
+
+
+def _bf16_round(a: np.ndarray) -> np.ndarray:
+    return torch.from_numpy(a).to(torch.bfloat16).to(torch.float32).numpy()
+
+
+# ------------------------------------------------------------------------------------------------
+# CFG + DDIM
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("eta", [0.0, 0.7])
+@pytest.mark.parametrize("frames", [1, 8])
+def test_ddim_cfg_step_fp32_exact(eta, frames):
+    from vface_b200 import ops
+    rng = np.random.default_rng(3)
+    sched = ok.make_schedule(10, eta)
+    shape = (frames, 4, 64, 64)
+    x = rng.standard_normal(shape).astype(np.float32)
+    eu = rng.standard_normal(shape).astype(np.float32)
+    ec = rng.standard_normal(shape).astype(np.float32)
+    nz = rng.standard_normal(shape).astype(np.float32)
+    for index in (0, 4, 9):
+        a_t, a_prev = sched["ddim_alphas"][index], sched["ddim_alphas_prev"][index]
+        sig, s1m = sched["ddim_sigmas"][index], sched["ddim_sqrt_one_minus_alphas"][index]
+        want_prev, want_x0 = ok.ddim_cfg_step(x, eu, ec, a_t, a_prev, sig, s1m, 3.0, nz if eta > 0 else None)
+        t = lambda a: torch.from_numpy(a).to(_dev())
+        got_prev, got_x0 = ops.ddim_cfg_step(t(x), t(eu), t(ec), a_t, a_prev, sig, s1m, 3.0, t(nz) if eta > 0 else None)
+        # fp32, same op order, no FMA contraction: bit-exact
+        assert np.array_equal(got_x0.cpu().numpy(), want_x0)
+        assert np.array_equal(got_prev.cpu().numpy(), want_prev)
+
+
+def test_ddim_cfg_step_bf16_eps():
+    from vface_b200 import ops
+    rng = np.random.default_rng(4)
+    sched = ok.make_schedule(50, 0.0)
+    shape = (4, 4, 64, 64)
+    x = rng.standard_normal(shape).astype(np.float32)
+    eu = _bf16_round(rng.standard_normal(shape).astype(np.float32))
+    ec = _bf16_round(rng.standard_normal(shape).astype(np.float32))
+    i = 20
+    args = (sched["ddim_alphas"][i], sched["ddim_alphas_prev"][i], sched["ddim_sigmas"][i], sched["ddim_sqrt_one_minus_alphas"][i], 3.0)
+    want_prev, want_x0 = ok.ddim_cfg_step(x, eu, ec, *args)
+    t = lambda a: torch.from_numpy(a).to(_dev())
+    got_prev, got_x0 = ops.ddim_cfg_step(t(x), t(eu).bfloat16(), t(ec).bfloat16(), *args)
+    assert np.array_equal(got_prev.cpu().numpy(), want_prev)
+    assert np.array_equal(got_x0.cpu().numpy(), want_x0)
+
+
+def test_ddim_invert_step():
+    from vface_b200 import ops
+    rng = np.random.default_rng(5)
+    acp = ok.make_schedule(50)["alphas_cumprod"]
+    shape = (2, 4, 64, 64)
+    x = rng.standard_normal(shape).astype(np.float32)
+    e = rng.standard_normal(shape).astype(np.float32)
+    a_cur, a_next = np.float32(acp[101]), np.float32(acp[121])
+    want = (x - np.sqrt(np.float32(1) - a_cur) * e) * np.sqrt(a_next) / np.sqrt(a_cur) + np.sqrt(np.float32(1) - a_next) * e
+    t = lambda a: torch.from_numpy(a).to(_dev())
+    got = ops.ddim_invert_step(t(x), t(e), a_cur, a_next)
+    assert np.array_equal(got.cpu().numpy(), want.astype(np.float32))
+
+
+# ------------------------------------------------------------------------------------------------
+# FSAI
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("d", [320, 640, 1280, 64, 160])
+@pytest.mark.parametrize("ratio", [0.8, 0.5, 0.25])
+def test_fsai_fp32(d, ratio):
+    from vface_b200 import ops
+    rng = np.random.default_rng(d)
+    b, n = 2, 37          # ragged: odd row count exercises the unpaired last row
+    donor = rng.standard_normal((b, n, d)).astype(np.float32)
+    dst = rng.standard_normal((b, n, d)).astype(np.float32)
+    want = ok.fsai_blend(donor, dst, ratio)
+    t = lambda a: torch.from_numpy(a).to(_dev())
+    got = ops.fsai_blend(t(donor), t(dst), ratio)
+    err = np.abs(got.cpu().numpy() - want).max()
+    assert err < 2e-5, err
+    # in place (the reference assigns into the slice), and the fused two-branch form
+    dst2 = rng.standard_normal((b, n, d)).astype(np.float32)
+    ta, tb = t(dst), t(dst2)
+    ops.fsai_blend2(t(donor), ta, tb, ratio)
+    assert np.abs(ta.cpu().numpy() - want).max() < 2e-5
+    assert np.abs(tb.cpu().numpy() - ok.fsai_blend(donor, dst2, ratio)).max() < 2e-5
+
+
+@pytest.mark.parametrize("d,n", [(320, 4096), (640, 1024), (1280, 256)])
+def test_fsai_bf16_module_shapes(d, n):
+    from vface_b200 import ops
+    rng = np.random.default_rng(n)
+    frames = 2
+    q = _bf16_round(rng.standard_normal((3 * frames, n, d)).astype(np.float32))
+    want_c = ok.fsai_blend(q[:frames], q[frames:2 * frames], 0.8)
+    want_r = ok.fsai_blend(q[:frames], q[2 * frames:], 0.8)
+    tq = torch.from_numpy(q).to(_dev()).bfloat16()
+    ops.fsai_blend2(tq[:frames], tq[frames:2 * frames], tq[2 * frames:], 0.8)   # in place on slices
+    got = tq.float().cpu().numpy()
+    assert np.array_equal(got[:frames], q[:frames])                              # donor untouched
+    assert np.abs(got[frames:2 * frames] - want_c).max() < BF16_TOL
+    assert np.abs(got[2 * frames:] - want_r).max() < BF16_TOL
+
+
+def test_fsai_linearity_and_identity():
+    """Size-independent properties at the full module size: split=d is the identity on dst,
+    split=0 returns the donor, and the op is linear in (donor, dst)."""
+    from vface_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(0)
+    donor = torch.randn(4, 4096, 320, generator=g).to(_dev())
+    dst = torch.randn(4, 4096, 320, generator=g).to(_dev())
+    assert (ops.fsai_blend(donor, dst, 1.0) - dst).abs().max().item() < 1e-5
+    assert (ops.fsai_blend(donor, dst, 0.0) - donor).abs().max().item() < 2e-5
+    a = ops.fsai_blend(donor, dst, 0.8)
+    b = ops.fsai_blend(2 * donor, 2 * dst, 0.8)
+    assert (b - 2 * a).abs().max().item() < 5e-5
+
+
+# ------------------------------------------------------------------------------------------------
+# flow warp + blend
+# ------------------------------------------------------------------------------------------------
+def _flows(rng, n, h, w, kind):
+    ys, xs = np.meshgrid(np.arange(h), np.arange(w), indexing="ij")
+    out = []
+    for i in range(n):
+        if kind == "smooth":
+            fx = 3 * np.sin(2 * np.pi * ys / h + i) + rng.normal(0, 0.5, (h, w))
+            fy = 3 * np.cos(2 * np.pi * xs / w - i) + rng.normal(0, 0.5, (h, w))
+        elif kind == "integer":
+            fx = rng.integers(-5, 6, (h, w)).astype(np.float64)
+            fy = rng.integers(-5, 6, (h, w)).astype(np.float64)
+        else:  # out of range: most taps clamp to the border
+            fx = rng.normal(0, 60, (h, w))
+            fy = rng.normal(0, 60, (h, w))
+        out.append(np.stack([fx, fy]).astype(np.float32))
+    return np.stack(out)
+
+
+@pytest.mark.parametrize("kind", ["smooth", "integer", "far"])
+@pytest.mark.parametrize("dtype", ["f32", "bf16"])
+def test_flow_warp_blend(kind, dtype):
+    from vface_b200 import ops
+    rng = np.random.default_rng(11)
+    frames, h, w, c = 4, 64, 64, 320
+    x = rng.standard_normal((frames, h * w, c)).astype(np.float32)
+    if dtype == "bf16":
+        x = _bf16_round(x)
+    flow = _flows(rng, frames - 1, h, w, kind)
+    want = ok.flow_warp_blend(x, flow, 0.8, h, w)
+    tx = torch.from_numpy(x).to(_dev())
+    if dtype == "bf16":
+        tx = tx.bfloat16()
+    got, taps = ops.flow_warp_blend(tx, torch.from_numpy(flow), 0.8, h, w, return_taps=True)
+    # floor indices: bit-exact against the oracle's fp32 chain (both ATen forms agree)
+    for i in range(frames - 1):
+        for form in ("cpu", "cuda"):
+            x0, y0, _, _ = ok.flow_taps(flow[i], h, w, form)
+            t = taps[i].cpu().numpy().reshape(h, w, 2)
+            assert np.array_equal(t[..., 0], x0) and np.array_equal(t[..., 1], y0)
+    err = np.abs(got.float().cpu().numpy() - want).max()
+    assert err < (BF16_TOL if dtype == "bf16" else 2e-6), err
+    assert np.array_equal(got[0].float().cpu().numpy(), x[0])
+
+
+def test_flow_warp_halo_equals_unsharded():
+    """Frame-sharded evaluation with a one-frame halo is bit-identical to the unsharded call."""
+    from vface_b200 import ops
+    rng = np.random.default_rng(12)
+    frames, h, w, c = 6, 64, 64, 320
+    x = torch.from_numpy(_bf16_round(rng.standard_normal((frames, h * w, c)).astype(np.float32))).to(_dev()).bfloat16()
+    flow = torch.from_numpy(_flows(rng, frames - 1, h, w, "smooth"))
+    full = ops.flow_warp_blend(x, flow, 0.8, h, w)
+    lo = ops.flow_warp_blend(x[:3], flow[:2], 0.8, h, w)
+    hi = ops.flow_warp_blend(x[3:], flow[2:], 0.8, h, w, prev_halo=x[2])
+    assert torch.equal(torch.cat([lo, hi]), full)
+
+
+def test_flow_warp_identity_flow():
+    from vface_b200 import ops
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(3, 1024, 640, generator=g).to(_dev())
+    flow = torch.zeros(2, 2, 32, 32)
+    got = ops.flow_warp_blend(x, flow, 0.8, 32, 32)
+    want = x.clone()
+    want[1:] = 0.8 * x[1:] + (1 - 0.8) * x[:-1]
+    assert (got - want).abs().max().item() < 1e-6
+
+
+# ------------------------------------------------------------------------------------------------
+# attention
+# ------------------------------------------------------------------------------------------------
+def _attn_case(rng, b, n_q, n_kv, heads, d, n_kv2=0, bf16=True):
+    mk = lambda n: rng.standard_normal((b, n, heads * d)).astype(np.float32)
+    q, k, v = mk(n_q), mk(n_kv), mk(n_kv)
+    k2 = mk(n_kv2) if n_kv2 else None
+    v2 = mk(n_kv2) if n_kv2 else None
+    if bf16:
+        q, k, v = _bf16_round(q), _bf16_round(k), _bf16_round(v)
+        if n_kv2:
+            k2, v2 = _bf16_round(k2), _bf16_round(v2)
+    return q, k, v, k2, v2
+
+
+ATTN_SHAPES = [
+    # b, n_q, n_kv, heads, d
+    (2, 256, 256, 8, 40),
+    (1, 1024, 1024, 2, 40),
+    (2, 1024, 1024, 8, 80),
+    (2, 256, 256, 8, 160),
+    (3, 64, 64, 8, 160),
+    (1, 200, 333, 4, 40),      # ragged rows and keys
+    (1, 128, 128, 2, 64),
+    (1, 128, 192, 2, 8),
+    (1, 384, 100, 2, 128),
+]
+
+
+@pytest.mark.parametrize("shape", ATTN_SHAPES)
+def test_attention_bf16(shape):
+    from vface_b200 import ops
+    b, n_q, n_kv, heads, d = shape
+    rng = np.random.default_rng(n_q * 7 + d)
+    q, k, v, _, _ = _attn_case(rng, b, n_q, n_kv, heads, d)
+    want = ok.attention(q, k, v, heads, d ** -0.5)
+    t = lambda a: torch.from_numpy(a).to(_dev()).bfloat16()
+    got = ops.attention(t(q), t(k), t(v), heads)
+    err = np.abs(got.float().cpu().numpy() - want).max()
+    assert err < BF16_TOL, err
+
+
+@pytest.mark.parametrize("shape", ATTN_SHAPES[:6])
+def test_attention_fp32(shape):
+    from vface_b200 import ops
+    b, n_q, n_kv, heads, d = shape
+    rng = np.random.default_rng(n_q * 5 + d)
+    q, k, v, _, _ = _attn_case(rng, b, n_q, n_kv, heads, d, bf16=False)
+    want = ok.attention(q, k, v, heads, d ** -0.5)
+    t = lambda a: torch.from_numpy(a).to(_dev())
+    got = ops.attention(t(q), t(k), t(v), heads)
+    err = np.abs(got.cpu().numpy() - want).max()
+    assert err < 2e-5, err
+
+
+@pytest.mark.parametrize("bf16", [True, False])
+def test_attention_concat_kv(bf16):
+    """Second K/V segment == attention over the concatenated keys (unpinned variant)."""
+    from vface_b200 import ops
+    rng = np.random.default_rng(99)
+    q, k, v, k2, v2 = _attn_case(rng, 2, 256, 256, 8, 40, n_kv2=320, bf16=bf16)
+    want = ok.attention(q, k, v, 8, 40 ** -0.5, k2, v2)
+    t = (lambda a: torch.from_numpy(a).to(_dev()).bfloat16()) if bf16 else (lambda a: torch.from_numpy(a).to(_dev()))
+    got = ops.attention(t(q), t(k), t(v), 8, k2=t(k2), v2=t(v2))
+    err = np.abs(got.float().cpu().numpy() - want).max()
+    assert err < (BF16_TOL if bf16 else 2e-5), err
+
+
+def test_attention_strided_qkv_and_large_logits():
+    """q/k/v as column slices of one fused projection buffer (row stride 3C) and logits large enough
+    to force the lazy O rescale."""
+    from vface_b200 import ops
+    rng = np.random.default_rng(5)
+    b, n, heads, d = 2, 512, 8, 40
+    c = heads * d
+    qkv = _bf16_round((rng.standard_normal((b, n, 3 * c)) * 3.0).astype(np.float32))
+    # make later keys systematically larger so the running max keeps moving
+    qkv[:, :, c:2 * c] *= np.linspace(0.2, 3.0, n, dtype=np.float32)[None, :, None]
+    qkv = _bf16_round(qkv)
+    q, k, v = qkv[..., :c], qkv[..., c:2 * c], qkv[..., 2 * c:]
+    want = ok.attention(q, k, v, heads, d ** -0.5)
+    t = torch.from_numpy(qkv).to(_dev()).bfloat16()
+    got = ops.attention(t[..., :c], t[..., c:2 * c], t[..., 2 * c:], heads)
+    err = np.abs(got.float().cpu().numpy() - want).max()
+    assert err < BF16_TOL, err
+
+
+def test_attention_full_size_vs_fp32_kernel():
+    """BASELINE.json config 3 shape (4096 tokens x 8 heads x d40): tcgen05 path against the fp32 CUDA
+    kernel (itself pinned to the oracle above), plus the row-stochastic property: with v = 1 the
+    output is exactly 1 up to bf16 rounding."""
+    from vface_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    b, n, heads, d = 2, 4096, 8, 40
+    q = torch.randn(b, n, heads * d, generator=g).to(_dev())
+    k = torch.randn(b, n, heads * d, generator=g).to(_dev())
+    v = torch.randn(b, n, heads * d, generator=g).to(_dev())
+    qb, kb, vb = q.bfloat16(), k.bfloat16(), v.bfloat16()
+    want = ops.attention(qb.float(), kb.float(), vb.float(), heads)
+    got = ops.attention(qb, kb, vb, heads)
+    assert (got.float() - want).abs().max().item() < BF16_TOL
+    ones = torch.ones_like(vb)
+    got1 = ops.attention(qb, kb, ones, heads)
+    assert (got1.float() - 1.0).abs().max().item() < 1e-2
+
+
+def test_errors_are_loud():
+    from vface_b200 import ops
+    x = torch.zeros(1, 64, 44, device=_dev(), dtype=torch.bfloat16)
+    with pytest.raises(RuntimeError):
+        ops.attention(x, x, x, 1)          # d=44 not a multiple of 8
+    with pytest.raises(RuntimeError):
+        ops.attention(torch.zeros(1, 4, 8), torch.zeros(1, 4, 8), torch.zeros(1, 4, 8), 1)   # CPU tensors
+    y = torch.zeros(1, 8, 96, device=_dev())
+    with pytest.raises(RuntimeError):
+        ops.fsai_blend(y, y.clone(), 0.8)   # d=96 = 2^5 * 3

@@ -1,0 +1,382 @@
+// Fused attention core on 5th-generation tensor cores (dtype VF_BF16 of vf_attn_fwd).
+//
+//   o = softmax(q k^T * scale) v   per (batch, head), q/k/v/o in the reference's native
+//   (batch, n, heads*d) layout (ldm/models/pnp_utils.py:270-286, ldm/modules/attention.py:203-220),
+//   optional second K/V segment concatenated along the key axis (injected target-frame K/V).
+//
+// Design (sm_100a):
+//   * one CTA = one 128-row query tile of one (batch, head); 6 warps:
+//       warp 0      TMA producer  (cp.async.bulk.tensor 4-D boxes, 128B swizzle, zero fill of the
+//                                  head-dim padding d -> 64k and of ragged row tails)
+//       warp 1      tcgen05.mma issuer + TMEM allocator (one elected lane issues)
+//       warps 2..5  softmax / correction / epilogue, one thread per query row (TMEM lane)
+//   * S = Q K^T      : tcgen05.mma  SS, M=128, N=BN, K=16 x ceil(d/16), fp32 accumulator in TMEM
+//   * P (bf16)       : written back to TMEM by the softmax threads (tcgen05.st), never to smem/HBM
+//   * O += P V       : tcgen05.mma  TS (A = P from TMEM), B = V tile in MN-major 128B-swizzled smem
+//   * online softmax in the exp2 domain with lazy rescaling of O (only when the running max moves
+//     by more than 2^8), so the correction pass is rare
+//   * K and V rings are separate 2-stage mbarrier pipelines; S_{j+1} is issued while the softmax of
+//     tile j runs, and two CTAs are resident per SM so their softmax and MMA phases interleave.
+//   * the head dimension is NOT padded in HBM: the TMA box is 64 elements wide over a tensor-map
+//     dimension of extent d, out-of-bounds columns are zero-filled in shared memory.
+//
+// TMEM columns: [0,BN) S fp32 | [BN, BN+BN/2) P bf16x2 | [BN+BN/2, +d_pad) O fp32.
+#include "vf_attn.cuh"
+#include "vf_sm100.cuh"
+
+#include <cuda.h>
+#include <cmath>
+
+namespace vf {
+
+using namespace sm100;
+
+constexpr int kTcThreads = 192;
+constexpr int kBM = 128;            // query rows per CTA
+constexpr float kRescaleThreshold = 8.0f;   // log2 units
+
+struct AttnTcParams {
+  __nv_bfloat16* o;
+  long long ld_o;
+  int heads, n_q, n_kv, n_kv2, d, d_pad, kb;   // kb = ceil(d / 64) 64-wide head-dim blocks
+  float scale_log2;                            // scale * log2(e)
+};
+
+struct __align__(8) TcBarriers {
+  uint64_t q_full;
+  uint64_t k_full[2], k_empty[2];
+  uint64_t v_full[2], v_empty[2];
+  uint64_t s_full, s_empty, p_full, o_done;
+  uint32_t tmem_base;
+};
+
+template <int BN, int kTmemCols>
+__global__ void __launch_bounds__(kTcThreads, 2)
+attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
+               const __grid_constant__ CUtensorMap map_v, const __grid_constant__ CUtensorMap map_k2,
+               const __grid_constant__ CUtensorMap map_v2, const AttnTcParams P) {
+  extern __shared__ unsigned char smem_dyn[];
+  __shared__ TcBarriers bars;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int q_tile = blockIdx.x;
+  const int bh = blockIdx.y;
+  const int b = bh / P.heads, h = bh - b * P.heads;
+
+  // ---- shared memory carve-up (1024-byte aligned tiles for the 128B swizzle) -------------------
+  const uint32_t dyn_base = smem_u32(smem_dyn);
+  const uint32_t tile_base = (dyn_base + 1023u) & ~1023u;
+  unsigned char* tiles = smem_dyn + (tile_base - dyn_base);
+  const uint32_t q_block_bytes = kBM * 128;
+  const uint32_t kv_block_bytes = BN * 128;
+  const uint32_t q_bytes = P.kb * q_block_bytes;
+  const uint32_t kv_bytes = P.kb * kv_block_bytes;
+  unsigned char* sQ = tiles;
+  unsigned char* sK = sQ + q_bytes;                 // 2 stages
+  unsigned char* sV = sK + 2 * kv_bytes;            // 2 stages
+
+  const int t1 = (P.n_kv + BN - 1) / BN;
+  const int t2 = (P.n_kv2 + BN - 1) / BN;
+  const int n_tiles = t1 + t2;
+
+  if (threadIdx.x == 0) {
+    mbar_init(&bars.q_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&bars.k_full[s], 1);
+      mbar_init(&bars.k_empty[s], 1);
+      mbar_init(&bars.v_full[s], 1);
+      mbar_init(&bars.v_empty[s], 1);
+    }
+    mbar_init(&bars.s_full, 1);
+    mbar_init(&bars.s_empty, 4);
+    mbar_init(&bars.p_full, 4);
+    mbar_init(&bars.o_done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<kTmemCols>(&bars.tmem_base);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = bars.tmem_base;
+  const uint32_t tm_s = tmem;
+  const uint32_t tm_p = tmem + BN;
+  const uint32_t tm_o = tmem + BN + BN / 2;
+
+  if (warp == 0) {
+    // =========================== TMA producer ====================================================
+    if (lane == 0) {
+      tma_prefetch_desc(&map_q);
+      tma_prefetch_desc(&map_k);
+      tma_prefetch_desc(&map_v);
+      mbar_arrive_expect_tx(&bars.q_full, q_bytes);
+      for (int kb = 0; kb < P.kb; ++kb)
+        tma_load_4d(sQ + kb * q_block_bytes, &map_q, &bars.q_full, kb * 64, h, q_tile * kBM, b);
+      for (int j = 0; j < n_tiles; ++j) {
+        const int st = j & 1;
+        const uint32_t use = (uint32_t)(j >> 1);
+        const bool seg2 = j >= t1;
+        const int row0 = (seg2 ? j - t1 : j) * BN;
+        const CUtensorMap* mk = seg2 ? &map_k2 : &map_k;
+        const CUtensorMap* mv = seg2 ? &map_v2 : &map_v;
+        mbar_wait(&bars.k_empty[st], (use & 1) ^ 1);
+        mbar_arrive_expect_tx(&bars.k_full[st], kv_bytes);
+        for (int kb = 0; kb < P.kb; ++kb)
+          tma_load_4d(sK + st * kv_bytes + kb * kv_block_bytes, mk, &bars.k_full[st], kb * 64, h, row0, b);
+        mbar_wait(&bars.v_empty[st], (use & 1) ^ 1);
+        mbar_arrive_expect_tx(&bars.v_full[st], kv_bytes);
+        for (int kb = 0; kb < P.kb; ++kb)
+          tma_load_4d(sV + st * kv_bytes + kb * kv_block_bytes, mv, &bars.v_full[st], kb * 64, h, row0, b);
+      }
+    }
+  } else if (warp == 1) {
+    // =========================== MMA issuer ======================================================
+    if (lane == 0) {
+      const uint32_t idesc_qk = make_idesc_bf16(kBM, BN, false);
+      const uint32_t idesc_pv = make_idesc_bf16(kBM, P.d_pad, true);
+      const int k_steps = P.d_pad / 16;
+      const uint32_t q_addr = smem_u32(sQ);
+      const uint32_t k_addr = smem_u32(sK);
+      const uint32_t v_addr = smem_u32(sV);
+
+      auto issue_qk = [&](int j) {
+        const int st = j & 1;
+        mbar_wait(&bars.k_full[st], (uint32_t)(j >> 1) & 1);
+        tc_fence_after();
+        for (int s = 0; s < k_steps; ++s) {
+          const uint32_t off_blk = (uint32_t)(s >> 2), off_in = (uint32_t)(s & 3) * 32u;
+          const uint64_t da = make_smem_desc_sw128(q_addr + off_blk * q_block_bytes + off_in, 16, 1024);
+          const uint64_t db = make_smem_desc_sw128(k_addr + st * kv_bytes + off_blk * kv_block_bytes + off_in, 16, 1024);
+          mma_ss(tm_s, da, db, idesc_qk, s > 0);
+        }
+        tc_commit(&bars.k_empty[st]);
+        tc_commit(&bars.s_full);
+      };
+
+      mbar_wait(&bars.q_full, 0);
+      issue_qk(0);
+      for (int j = 0; j < n_tiles; ++j) {
+        if (j + 1 < n_tiles) {
+          mbar_wait(&bars.s_empty, (uint32_t)j & 1);     // softmax has S_j in registers
+          issue_qk(j + 1);
+        }
+        const int st = j & 1;
+        mbar_wait(&bars.v_full[st], (uint32_t)(j >> 1) & 1);
+        mbar_wait(&bars.p_full, (uint32_t)j & 1);        // P_j in TMEM, O rescaled if needed
+        tc_fence_after();
+#pragma unroll 1
+        for (int s = 0; s < BN / 16; ++s) {
+          // B = V tile, MN-major: 64 head-dim elements contiguous (128 B) per key row, 8-row groups
+          // 1024 B apart (SBO), further 64-wide head-dim blocks kv_block_bytes apart (LBO).
+          const uint64_t db = make_smem_desc_sw128(v_addr + st * kv_bytes + (uint32_t)s * 2048u, kv_block_bytes, 1024);
+          mma_ts(tm_o, tm_p + (uint32_t)s * 8u, db, idesc_pv, (j > 0) || (s > 0));
+        }
+        tc_commit(&bars.v_empty[st]);
+        tc_commit(&bars.o_done);
+      }
+    }
+  } else {
+    // =========================== softmax / correction / epilogue ================================
+    const int quarter = warp & 3;                        // TMEM lane quarter this warp may touch
+    const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
+    const int row = q_tile * kBM + quarter * 32 + lane;  // query row owned by this thread
+    float m_ref = 0.0f, l = 0.0f;
+
+    for (int j = 0; j < n_tiles; ++j) {
+      const bool seg2 = j >= t1;
+      const int row0 = (seg2 ? j - t1 : j) * BN;
+      const int valid = min(BN, (seg2 ? P.n_kv2 : P.n_kv) - row0);
+
+      mbar_wait(&bars.s_full, (uint32_t)j & 1);
+      tc_fence_after();
+      uint32_t sr[BN / 32][32];
+#pragma unroll
+      for (int c = 0; c < BN / 32; ++c) tmem_ld_x32(tm_s + lane_off + c * 32, sr[c]);
+      tmem_wait_ld();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars.s_empty);
+
+      if (valid < BN) {
+#pragma unroll
+        for (int c = 0; c < BN / 32; ++c)
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (c * 32 + i >= valid) sr[c][i] = 0xff800000u;   // -inf
+      }
+      float mx0 = __uint_as_float(sr[0][0]), mx1 = __uint_as_float(sr[0][1]);
+#pragma unroll
+      for (int c = 0; c < BN / 32; ++c)
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          mx0 = fmaxf(mx0, __uint_as_float(sr[c][i]));
+          mx1 = fmaxf(mx1, __uint_as_float(sr[c][i + 1]));
+        }
+      const float cand = fmaxf(mx0, mx1) * P.scale_log2;
+      float alpha = 1.0f;
+      bool need = false;
+      if (j == 0) {
+        m_ref = cand;
+      } else if (cand > m_ref + kRescaleThreshold) {
+        alpha = ex2_approx(m_ref - cand);
+        m_ref = cand;
+        need = true;
+      }
+      if (j > 0) {
+        // PV_{j-1} retired (it was issued before S_j was consumed, so this never stalls in steady
+        // state): the P columns and O are ours again.
+        mbar_wait(&bars.o_done, (uint32_t)(j - 1) & 1);
+        tc_fence_after();
+      }
+      float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f, sum3 = 0.f;
+#pragma unroll
+      for (int g = 0; g < BN / 64; ++g) {            // 64 score columns -> 32 packed bf16x2 columns
+        uint32_t pk[32];
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc)
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            const int c = g * 2 + cc;
+            const float p0 = ex2_approx(fmaf(__uint_as_float(sr[c][i + 0]), P.scale_log2, -m_ref));
+            const float p1 = ex2_approx(fmaf(__uint_as_float(sr[c][i + 1]), P.scale_log2, -m_ref));
+            const float p2 = ex2_approx(fmaf(__uint_as_float(sr[c][i + 2]), P.scale_log2, -m_ref));
+            const float p3 = ex2_approx(fmaf(__uint_as_float(sr[c][i + 3]), P.scale_log2, -m_ref));
+            sum0 += p0; sum1 += p1; sum2 += p2; sum3 += p3;
+            pk[cc * 16 + i / 2 + 0] = pack_bf16(p0, p1);
+            pk[cc * 16 + i / 2 + 1] = pack_bf16(p2, p3);
+          }
+        tmem_st_x32(tm_p + lane_off + g * 32, pk);
+      }
+      l = l * alpha + ((sum0 + sum1) + (sum2 + sum3));
+      if (j > 0 && __any_sync(0xffffffffu, need)) {
+        for (int c = 0; c < P.d; c += 8) {
+          uint32_t o8[8];
+          tmem_ld_x8(tm_o + lane_off + c, o8);
+          tmem_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 8; ++i) o8[i] = __float_as_uint(__uint_as_float(o8[i]) * alpha);
+          tmem_st_x8(tm_o + lane_off + c, o8);
+        }
+      }
+      tmem_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars.p_full);
+    }
+
+    // ---- epilogue: O / l -> bf16 -> global ------------------------------------------------------
+    mbar_wait(&bars.o_done, (uint32_t)(n_tiles - 1) & 1);
+    tc_fence_after();
+    const float inv_l = 1.0f / l;
+    __nv_bfloat16* orow = P.o + ((long long)b * P.n_q + row) * P.ld_o + (long long)h * P.d;
+    for (int c = 0; c < P.d; c += 8) {
+      uint32_t o8[8];
+      tmem_ld_x8(tm_o + lane_off + c, o8);
+      tmem_wait_ld();
+      if (row < P.n_q) {
+        uint4 pkd;
+        pkd.x = pack_bf16(__uint_as_float(o8[0]) * inv_l, __uint_as_float(o8[1]) * inv_l);
+        pkd.y = pack_bf16(__uint_as_float(o8[2]) * inv_l, __uint_as_float(o8[3]) * inv_l);
+        pkd.z = pack_bf16(__uint_as_float(o8[4]) * inv_l, __uint_as_float(o8[5]) * inv_l);
+        pkd.w = pack_bf16(__uint_as_float(o8[6]) * inv_l, __uint_as_float(o8[7]) * inv_l);
+        *reinterpret_cast<uint4*>(orow + c) = pkd;
+      }
+    }
+    tc_fence_before();
+  }
+
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<kTmemCols>(tmem);
+  }
+}
+
+// ---- host side --------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+      qres != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = reinterpret_cast<EncodeTiledFn>(p);
+  return fn;
+}
+
+// (batch, n, heads*d) bf16 with row stride ld  ->  4-D map {d, heads, n, batch}, box {64, 1, rows, 1}.
+static int make_map(CUtensorMap* m, const void* base, int batch, int heads, int n, int d, long long ld, int box_rows) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return fail("vf_attn_fwd: cuTensorMapEncodeTiled entry point not found");
+  cuuint64_t dims[4] = {(cuuint64_t)d, (cuuint64_t)heads, (cuuint64_t)n, (cuuint64_t)batch};
+  cuuint64_t strides[3] = {(cuuint64_t)d * 2, (cuuint64_t)ld * 2, (cuuint64_t)ld * 2 * (cuuint64_t)n};
+  cuuint32_t box[4] = {64, 1, (cuuint32_t)box_rows, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail("vf_attn_fwd: cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return 0;
+}
+
+template <int BN, int kTmemCols>
+static int launch_tc(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const CUtensorMap& mk2,
+                     const CUtensorMap& mv2, const AttnTcParams& P, int batch, cudaStream_t st) {
+  const size_t smem = 1024 + (size_t)P.kb * (kBM * 128 + 4 * BN * 128);
+  static bool attr = false;
+  if (!attr) {
+    VF_CUDA_TRY(cudaFuncSetAttribute(attn_tc_kernel<BN, kTmemCols>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr = true;
+  }
+  dim3 grid((P.n_q + kBM - 1) / kBM, batch * P.heads);
+  attn_tc_kernel<BN, kTmemCols><<<grid, kTcThreads, smem, st>>>(mq, mk, mv, mk2, mv2, P);
+  return check_cuda(cudaGetLastError(), "attn_tc_kernel launch");
+}
+
+int launch_attn_tc(const void* q, const void* k, const void* v, void* o, int batch, int heads, int n_q, int n_kv,
+                   int d, long long ld_q, long long ld_k, long long ld_v, long long ld_o, float scale,
+                   const void* k2, const void* v2, int n_kv2, long long ld_k2, long long ld_v2, cudaStream_t st) {
+  if (d % 8 || d < 8 || d > 192) return fail("vf_attn_fwd(bf16): d_head=%d must be a multiple of 8 in [8, 192]", d);
+  const long long lds[4] = {ld_q, ld_k, ld_v, ld_o};
+  for (long long ld : lds)
+    if (ld % 8 || ld < (long long)heads * d) return fail("vf_attn_fwd(bf16): row strides must be multiples of 8 elements and >= heads*d");
+  const void* ptrs[4] = {q, k, v, o};
+  for (const void* p : ptrs)
+    if (reinterpret_cast<uintptr_t>(p) & 15) return fail("vf_attn_fwd(bf16): pointers must be 16-byte aligned");
+  const bool has2 = k2 != nullptr && n_kv2 > 0;
+  if (has2) {
+    if (!v2) return fail("vf_attn_fwd: k2 given without v2");
+    if (ld_k2 % 8 || ld_v2 % 8 || ld_k2 < (long long)heads * d || ld_v2 < (long long)heads * d)
+      return fail("vf_attn_fwd(bf16): bad k2/v2 row strides");
+    if ((reinterpret_cast<uintptr_t>(k2) & 15) || (reinterpret_cast<uintptr_t>(v2) & 15))
+      return fail("vf_attn_fwd(bf16): k2/v2 must be 16-byte aligned");
+  }
+  AttnTcParams P;
+  P.o = reinterpret_cast<__nv_bfloat16*>(o);
+  P.ld_o = ld_o;
+  P.heads = heads; P.n_q = n_q; P.n_kv = n_kv; P.n_kv2 = has2 ? n_kv2 : 0;
+  P.d = d; P.d_pad = (d + 15) / 16 * 16; P.kb = (d + 63) / 64;
+  P.scale_log2 = scale * 1.4426950408889634f;
+  const int bn = d <= 64 ? 128 : 64;
+  CUtensorMap mq, mk, mv, mk2, mv2;
+  if (int rc = make_map(&mq, q, batch, heads, n_q, d, ld_q, kBM)) return rc;
+  if (int rc = make_map(&mk, k, batch, heads, n_kv, d, ld_k, bn)) return rc;
+  if (int rc = make_map(&mv, v, batch, heads, n_kv, d, ld_v, bn)) return rc;
+  if (has2) {
+    if (int rc = make_map(&mk2, k2, batch, heads, n_kv2, d, ld_k2, bn)) return rc;
+    if (int rc = make_map(&mv2, v2, batch, heads, n_kv2, d, ld_v2, bn)) return rc;
+  } else {
+    mk2 = mk;
+    mv2 = mv;
+  }
+  if (bn == 128) return launch_tc<128, 256>(mq, mk, mv, mk2, mv2, P, batch, st);
+  if (64 + 32 + P.d_pad <= 256) return launch_tc<64, 256>(mq, mk, mv, mk2, mv2, P, batch, st);
+  return launch_tc<64, 512>(mq, mk, mv, mk2, mv2, P, batch, st);
+}
+
+}  // namespace vf

@@ -1,0 +1,222 @@
+"""Tensor-level entry points of the four hot-path kernels.
+
+Every function takes CUDA torch tensors, passes raw device pointers and the current stream through
+the C-ABI (include/vface_b200.h) and returns torch tensors.  PyTorch is only the allocator and stream
+provider here; there is no eager/CPU fallback -- CPU tensors or a missing library raise.
+"""
+from __future__ import annotations
+
+from typing import Optional, Sequence, Union
+
+import torch
+
+from . import _lib
+from ._lib import VF_BF16, VF_F32
+
+# number of kernels launched through the C-ABI since import (bench.py reports it as gpu_launches)
+launch_count = 0
+
+
+def _count(n=1):
+    global launch_count
+    launch_count += n
+
+
+def _code(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return VF_F32
+    if t.dtype == torch.bfloat16:
+        return VF_BF16
+    raise TypeError(f"vface_b200 kernels take float32 or bfloat16 tensors, got {t.dtype}")
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("vface_b200 ops need CUDA tensors: there is no CPU fallback")
+
+
+def _stream(t: torch.Tensor) -> int:
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _rows3(t: torch.Tensor, name: str):
+    """(batch, n, c) tensor with unit channel stride and uniform row stride -> (ld, batch, n, c)."""
+    if t.dim() != 3:
+        raise ValueError(f"{name}: expected (batch, n, c), got {tuple(t.shape)}")
+    b, n, c = t.shape
+    if t.stride(2) != 1 or (b > 1 and t.stride(0) != n * t.stride(1)):
+        raise ValueError(f"{name}: need unit channel stride and batch stride == n * row stride, got strides {t.stride()}")
+    return t.stride(1), b, n, c
+
+
+def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, scale: Optional[float] = None,
+              k2: Optional[torch.Tensor] = None, v2: Optional[torch.Tensor] = None,
+              out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """softmax(q k^T * scale) v per head on the (batch, n, heads*d) layout
+    (ldm/models/pnp_utils.py:270-286).  k2/v2: optional concatenated key/value segment."""
+    _need_cuda(q, k, v, k2, v2, out)
+    ld_q, b, n_q, c = _rows3(q, "q")
+    ld_k, bk, n_kv, ck = _rows3(k, "k")
+    ld_v, bv, n_v, cv = _rows3(v, "v")
+    if (bk, ck) != (b, c) or (bv, n_v, cv) != (b, n_kv, c) or c % heads:
+        raise ValueError(f"attention: inconsistent shapes q{tuple(q.shape)} k{tuple(k.shape)} v{tuple(v.shape)} heads={heads}")
+    if not (q.dtype == k.dtype == v.dtype):
+        raise TypeError("attention: q, k, v must share a dtype")
+    d = c // heads
+    if scale is None:
+        scale = d ** -0.5
+    if out is None:
+        out = torch.empty((b, n_q, c), dtype=q.dtype, device=q.device)
+    ld_o, bo, no, co = _rows3(out, "out")
+    if (bo, no, co) != (b, n_q, c) or out.dtype != q.dtype:
+        raise ValueError("attention: bad out tensor")
+    p_k2 = p_v2 = None
+    n_kv2 = ld_k2 = ld_v2 = 0
+    if k2 is not None:
+        ld_k2, b2, n_kv2, c2 = _rows3(k2, "k2")
+        ld_v2, b3, n3, c3 = _rows3(v2, "v2")
+        if (b2, c2) != (b, c) or (b3, n3, c3) != (b, n_kv2, c) or k2.dtype != q.dtype or v2.dtype != q.dtype:
+            raise ValueError("attention: bad k2/v2")
+        p_k2, p_v2 = k2.data_ptr(), v2.data_ptr()
+    lib = _lib.load()
+    rc = lib.vf_attn_fwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), b, heads, n_q, n_kv, d,
+                         ld_q, ld_k, ld_v, ld_o, float(scale), p_k2, p_v2, n_kv2, ld_k2, ld_v2,
+                         _code(q), _stream(q))
+    _lib.check(rc, "vf_attn_fwd")
+    _count()
+    return out
+
+
+def fsai_blend(donor: torch.Tensor, dst: torch.Tensor, split_ratio: float = 0.8,
+               out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """combine_fft_high_low(q1=donor, q2=dst, split_ratio) (scripts/face_swap_utils.py:425-464).
+    out=None returns a new tensor; out=dst reproduces the reference's in-place slice assignment."""
+    _need_cuda(donor, dst, out)
+    ld_d, b, n, d = _rows3(donor, "donor")
+    ld_s, b2, n2, d2 = _rows3(dst, "dst")
+    if (b, n, d) != (b2, n2, d2) or donor.dtype != dst.dtype:
+        raise ValueError("fsai_blend: donor/dst mismatch")
+    if out is None:
+        out = torch.empty((b, n, d), dtype=dst.dtype, device=dst.device)
+    ld_o, b3, n3, d3 = _rows3(out, "out")
+    if (b3, n3, d3) != (b, n, d) or out.dtype != dst.dtype:
+        raise ValueError("fsai_blend: bad out tensor")
+    split = int(d * split_ratio)
+    lib = _lib.load()
+    rc = lib.vf_fsai_blend(donor.data_ptr(), dst.data_ptr(), out.data_ptr(), b * n, d, split,
+                           ld_d, ld_s, ld_o, _code(dst), _stream(dst))
+    _lib.check(rc, "vf_fsai_blend")
+    _count()
+    return out
+
+
+def fsai_blend2(donor: torch.Tensor, dst_a: torch.Tensor, dst_b: torch.Tensor, split_ratio: float = 0.8,
+                out_a: Optional[torch.Tensor] = None, out_b: Optional[torch.Tensor] = None):
+    """Both branches of one tensor in one launch (ldm/models/pnp_utils.py:195+198 or :196+199):
+    out_a = FSAI(donor, dst_a), out_b = FSAI(donor, dst_b); outputs default to in place."""
+    _need_cuda(donor, dst_a, dst_b, out_a, out_b)
+    out_a = dst_a if out_a is None else out_a
+    out_b = dst_b if out_b is None else out_b
+    ld_d, b, n, d = _rows3(donor, "donor")
+    lds = []
+    for name, t in (("dst_a", dst_a), ("out_a", out_a), ("dst_b", dst_b), ("out_b", out_b)):
+        ld, bb, nn, dd = _rows3(t, name)
+        if (bb, nn, dd) != (b, n, d) or t.dtype != donor.dtype:
+            raise ValueError(f"fsai_blend2: {name} mismatch")
+        lds.append(ld)
+    split = int(d * split_ratio)
+    lib = _lib.load()
+    rc = lib.vf_fsai_blend2(donor.data_ptr(), dst_a.data_ptr(), out_a.data_ptr(), dst_b.data_ptr(), out_b.data_ptr(),
+                            b * n, d, split, ld_d, lds[0], lds[1], lds[2], lds[3], _code(donor), _stream(donor))
+    _lib.check(rc, "vf_fsai_blend2")
+    _count()
+    return out_a, out_b
+
+
+def _as_flow(flow: Union[torch.Tensor, Sequence[torch.Tensor]], device) -> torch.Tensor:
+    if isinstance(flow, (list, tuple)):
+        flow = torch.cat([f.reshape(1, 2, f.shape[-2], f.shape[-1]) for f in flow], dim=0)
+    return flow.to(device=device, dtype=torch.float32).contiguous()
+
+
+def flow_warp_blend(x: torch.Tensor, flow, alpha: float, h: int, w: int,
+                    prev_halo: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
+                    return_taps: bool = False):
+    """align_by_flow (scripts/temporal_flow.py:222-237) on the token layout (frames, h*w, c).
+    flow: (n_flow, 2, h, w) fp32 tensor or the reference's list of (1, 2, h, w) tensors."""
+    _need_cuda(x, prev_halo, out)
+    ld_x, frames, n, c = _rows3(x, "x")
+    if n != h * w:
+        raise ValueError(f"flow_warp_blend: n={n} != h*w={h * w}")
+    n_flow = frames if prev_halo is not None else frames - 1
+    fl = None
+    if n_flow > 0:
+        fl = _as_flow(flow, x.device)
+        if tuple(fl.shape) != (n_flow, 2, h, w):
+            raise ValueError(f"flow_warp_blend: flow shape {tuple(fl.shape)} != {(n_flow, 2, h, w)} "
+                             "(flow must be at feature resolution, SURVEY.md F5)")
+    if out is None:
+        out = torch.empty((frames, n, c), dtype=x.dtype, device=x.device)
+    ld_o, fo, no, co = _rows3(out, "out")
+    if (fo, no, co) != (frames, n, c) or out.dtype != x.dtype:
+        raise ValueError("flow_warp_blend: bad out tensor")
+    ld_h = 0
+    p_h = None
+    if prev_halo is not None:
+        if prev_halo.dim() != 2 or tuple(prev_halo.shape) != (n, c) or prev_halo.stride(1) != 1 or prev_halo.dtype != x.dtype:
+            raise ValueError("flow_warp_blend: prev_halo must be (h*w, c) with unit channel stride")
+        ld_h = prev_halo.stride(0)
+        p_h = prev_halo.data_ptr()
+    taps = None
+    if return_taps:
+        taps = torch.empty((max(n_flow, 1), n, 2), dtype=torch.int32, device=x.device)
+    lib = _lib.load()
+    rc = lib.vf_flow_warp_blend(x.data_ptr(), p_h, fl.data_ptr() if fl is not None else None, out.data_ptr(),
+                                frames, h, w, c, ld_x, ld_h, ld_o, float(alpha), _code(x),
+                                taps.data_ptr() if taps is not None else None, _stream(x))
+    _lib.check(rc, "vf_flow_warp_blend")
+    _count()
+    return (out, taps) if return_taps else out
+
+
+def ddim_cfg_step(x: torch.Tensor, e_uncond: torch.Tensor, e_cond: torch.Tensor,
+                  a_t: float, a_prev: float, sigma_t: float, sqrt_one_minus_at: float, cfg_scale: float,
+                  noise: Optional[torch.Tensor] = None):
+    """CFG + DDIM update (ldm/models/diffusion/ddim_w_inv.py:666, :686, :696-700) -> (x_prev, pred_x0)."""
+    _need_cuda(x, e_uncond, e_cond, noise)
+    if x.dtype != torch.float32 or not x.is_contiguous():
+        raise ValueError("ddim_cfg_step: x must be contiguous float32")
+    if not (e_uncond.is_contiguous() and e_cond.is_contiguous()) or e_uncond.dtype != e_cond.dtype:
+        raise ValueError("ddim_cfg_step: e_uncond/e_cond must be contiguous and share a dtype")
+    if e_uncond.numel() != x.numel() or e_cond.numel() != x.numel():
+        raise ValueError("ddim_cfg_step: size mismatch")
+    if noise is not None and (noise.dtype != torch.float32 or not noise.is_contiguous() or noise.numel() != x.numel()):
+        raise ValueError("ddim_cfg_step: noise must be contiguous float32 of x's size")
+    x_prev = torch.empty_like(x)
+    pred_x0 = torch.empty_like(x)
+    lib = _lib.load()
+    rc = lib.vf_ddim_cfg_step(x.data_ptr(), e_uncond.data_ptr(), e_cond.data_ptr(), x_prev.data_ptr(), pred_x0.data_ptr(),
+                              float(a_t), float(a_prev), float(sigma_t), float(sqrt_one_minus_at), float(cfg_scale),
+                              noise.data_ptr() if noise is not None else None, x.numel(), _code(e_cond), _stream(x))
+    _lib.check(rc, "vf_ddim_cfg_step")
+    _count()
+    return x_prev, pred_x0
+
+
+def ddim_invert_step(x: torch.Tensor, e_cond: torch.Tensor, a_cur: float, a_next: float,
+                     e_uncond: Optional[torch.Tensor] = None, cfg_scale: float = 1.0) -> torch.Tensor:
+    """Forward-DDIM update of ddim_invert (ldm/models/diffusion/ddim_w_inv.py:426-449)."""
+    _need_cuda(x, e_cond, e_uncond)
+    if x.dtype != torch.float32 or not x.is_contiguous() or not e_cond.is_contiguous() or e_cond.numel() != x.numel():
+        raise ValueError("ddim_invert_step: x must be contiguous float32 and e_cond contiguous of the same size")
+    if e_uncond is not None and (not e_uncond.is_contiguous() or e_uncond.dtype != e_cond.dtype or e_uncond.numel() != x.numel()):
+        raise ValueError("ddim_invert_step: bad e_uncond")
+    x_next = torch.empty_like(x)
+    lib = _lib.load()
+    rc = lib.vf_ddim_invert_step(x.data_ptr(), e_uncond.data_ptr() if e_uncond is not None else None, e_cond.data_ptr(),
+                                 x_next.data_ptr(), float(a_cur), float(a_next), float(cfg_scale), x.numel(),
+                                 _code(e_cond), _stream(x))
+    _lib.check(rc, "vf_ddim_invert_step")
+    _count()
+    return x_next
