@@ -1,0 +1,172 @@
+"""Transformer blocks of the REFace UNet, backed by the vface_b200 attention kernel.
+
+Host-side mirror of REFace/ldm/modules/attention.py: CrossAttention :152-221,
+BasicTransformerBlock :224-243, SpatialTransformer :246-288, GEGLU/FeedForward :37-64.  Class names,
+constructor arguments, sub-module names and therefore state-dict keys are the reference's, so
+`last.ckpt` loads unchanged; the forward passes are re-designed:
+
+  * q, k, v come from ONE projection GEMM over a cached concatenated weight and stay in the
+    (batch, n, heads*d) layout -- the attention kernel indexes heads itself, so the reference's
+    three 'b n (h d) -> (b h) n d' rearrange copies and the N x N `sim` / `attn` tensors never exist;
+  * self-attention runs in vf_attn_fwd (tcgen05 for bf16, fp32 kernel for fp32 parity runs);
+  * cross-attention against a single context token (the VFace conditioning is (B, 1, 768)) is a
+    softmax over one key == 1, so it folds to to_out(to_v(context)) broadcast over tokens
+    (SURVEY.md row a11); longer contexts go through the same attention kernel.
+"""
+from __future__ import annotations
+
+from inspect import isfunction
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from ... import ops
+from .diffusionmodules.util import zero_module
+
+
+def exists(val):
+    return val is not None
+
+
+def default(val, d):
+    if exists(val):
+        return val
+    return d() if isfunction(d) else d
+
+
+class GEGLU(nn.Module):
+    def __init__(self, dim_in, dim_out):
+        super().__init__()
+        self.proj = nn.Linear(dim_in, dim_out * 2)
+
+    def forward(self, x):
+        x, gate = self.proj(x).chunk(2, dim=-1)
+        return x * F.gelu(gate)
+
+
+class FeedForward(nn.Module):
+    def __init__(self, dim, dim_out=None, mult=4, glu=False, dropout=0.):
+        super().__init__()
+        inner_dim = int(dim * mult)
+        dim_out = default(dim_out, dim)
+        project_in = GEGLU(dim, inner_dim) if glu else nn.Sequential(nn.Linear(dim, inner_dim), nn.GELU())
+        self.net = nn.Sequential(project_in, nn.Dropout(dropout), nn.Linear(inner_dim, dim_out))
+
+    def forward(self, x):
+        return self.net(x)
+
+
+def Normalize(in_channels):
+    return torch.nn.GroupNorm(num_groups=32, num_channels=in_channels, eps=1e-6, affine=True)
+
+
+class CrossAttention(nn.Module):
+    """Parameters: to_q/to_k/to_v.weight (no bias), to_out.0.{weight,bias} (reference :152-177)."""
+
+    def __init__(self, query_dim, context_dim=None, heads=8, dim_head=64, dropout=0., sep_head_att=False):
+        super().__init__()
+        if sep_head_att:
+            raise NotImplementedError("sep_head_att is not used by the VFace configuration")
+        inner_dim = dim_head * heads
+        context_dim = default(context_dim, query_dim)
+        self.scale = dim_head ** -0.5
+        self.heads = heads
+        self.dim_head = dim_head
+        self.head_splits = [6, 2]
+        self.to_q = nn.Linear(query_dim, inner_dim, bias=False)
+        self.to_k = nn.Linear(context_dim, inner_dim, bias=False)
+        self.to_v = nn.Linear(context_dim, inner_dim, bias=False)
+        self.to_out = nn.Sequential(nn.Linear(inner_dim, query_dim), nn.Dropout(dropout))
+        self._wqkv = None
+        self._wqkv_key = None
+
+    # -- fused projection -------------------------------------------------------------------------
+    def fused_qkv_weight(self):
+        """[Wq; Wk; Wv] (3*inner, query_dim), cached until any of the three parameters changes."""
+        ws = (self.to_q.weight, self.to_k.weight, self.to_v.weight)
+        key = tuple((w.data_ptr(), w._version, w.dtype, w.device) for w in ws)
+        if self._wqkv is None or self._wqkv_key != key:
+            self._wqkv = torch.cat([w.detach() for w in ws], dim=0).contiguous()
+            self._wqkv_key = key
+        return self._wqkv
+
+    def project_qkv(self, x):
+        """Self-attention projections in one GEMM: returns column-slice views q, k, v of a
+        (batch, n, 3*inner) buffer (row stride 3*inner; the kernels take row strides)."""
+        inner = self.heads * self.dim_head
+        qkv = F.linear(x, self.fused_qkv_weight())
+        return qkv[..., :inner], qkv[..., inner:2 * inner], qkv[..., 2 * inner:]
+
+    def attend(self, q, k, v):
+        """softmax(q k^T * scale) v, heads indexed inside the kernel (reference :270-286 / :206-220)."""
+        return ops.attention(q, k, v, self.heads, self.scale)
+
+    def forward(self, x, context=None, mask=None):
+        if exists(mask):
+            raise NotImplementedError("attention masks are not used on the VFace hot path")
+        if context is None:
+            q, k, v = self.project_qkv(x)
+            return self.to_out(self.attend(q, k, v))
+        if context.shape[-1] == 768 * 2:
+            raise NotImplementedError("split clip/landmark contexts (1536-wide) are not used by the VFace configuration")
+        if context.shape[1] == 1:
+            # one key: softmax == 1 exactly, out = to_out(to_v(context)) for every query token
+            row = self.to_out(self.to_v(context))             # (b, 1, query_dim)
+            return row.expand(-1, x.shape[1], -1)
+        q = self.to_q(x)
+        k = self.to_k(context)
+        v = self.to_v(context)
+        return self.to_out(self.attend(q, k, v))
+
+
+class BasicTransformerBlock(nn.Module):
+    def __init__(self, dim, n_heads, d_head, dropout=0., context_dim=None, gated_ff=True, checkpoint=True,
+                 sep_head_att=False):
+        super().__init__()
+        self.attn1 = CrossAttention(query_dim=dim, heads=n_heads, dim_head=d_head, dropout=dropout)
+        self.ff = FeedForward(dim, dropout=dropout, glu=gated_ff)
+        self.attn2 = CrossAttention(query_dim=dim, context_dim=context_dim, heads=n_heads, dim_head=d_head,
+                                    dropout=dropout, sep_head_att=sep_head_att)
+        self.norm1 = nn.LayerNorm(dim)
+        self.norm2 = nn.LayerNorm(dim)
+        self.norm3 = nn.LayerNorm(dim)
+        self.checkpoint = checkpoint      # gradient checkpointing is a training device; inference ignores it
+
+    def forward(self, x, context=None):
+        return self._forward(x, context)
+
+    def _forward(self, x, context=None):
+        # self.attn1(...) goes through the instance attribute so that the VFace hooks, which assign
+        # module.forward (ldm/models/pnp_utils.py:289-339), take effect exactly as in the reference.
+        x = self.attn1(self.norm1(x)) + x
+        x = self.attn2(self.norm2(x), context=context) + x
+        x = self.ff(self.norm3(x)) + x
+        return x
+
+
+class SpatialTransformer(nn.Module):
+    """GroupNorm -> 1x1 conv -> tokens -> transformer blocks -> 1x1 conv (zero-init) -> + input
+    (reference :246-288).  With channels_last activations 'b c h w -> b (h w) c' is a view."""
+
+    def __init__(self, in_channels, n_heads, d_head, depth=1, dropout=0., context_dim=None, sep_head_att=False,
+                 head_splits=None):
+        super().__init__()
+        self.in_channels = in_channels
+        inner_dim = n_heads * d_head
+        self.norm = Normalize(in_channels)
+        self.proj_in = nn.Conv2d(in_channels, inner_dim, kernel_size=1, stride=1, padding=0)
+        self.transformer_blocks = nn.ModuleList(
+            [BasicTransformerBlock(inner_dim, n_heads, d_head, dropout=dropout, context_dim=context_dim,
+                                   sep_head_att=sep_head_att) for _ in range(depth)])
+        self.proj_out = zero_module(nn.Conv2d(inner_dim, in_channels, kernel_size=1, stride=1, padding=0))
+
+    def forward(self, x, context=None):
+        b, c, h, w = x.shape
+        x_in = x
+        x = self.proj_in(self.norm(x))
+        x = x.permute(0, 2, 3, 1).reshape(b, h * w, -1)          # free for channels_last
+        for block in self.transformer_blocks:
+            x = block(x, context=context)
+        x = x.reshape(b, h, w, -1).permute(0, 3, 1, 2)
+        return self.proj_out(x) + x_in
