@@ -200,8 +200,12 @@ def make_schedule(S: int, eta: float = 0.0, n_ddpm: int = 1000, linear_start=0.0
     steps = np.asarray(list(range(0, n_ddpm, c))) + 1
     alphas = acp[steps]
     alphas_prev = np.asarray([acp[0]] + acp[steps[:-1]].tolist(), dtype=F32)
+    # util.py:70 mixes a fp32 torch tensor (alphas) with a fp64 numpy array (alphas_prev).  numpy defers
+    # `ndarray / Tensor` to Tensor.__rtruediv__, which torch evaluates as reciprocal(self) * other, so
+    # 1/(1 - alphas) is formed in fp32 and only then promoted; every other term is fp64.
     a64, ap64 = alphas.astype(np.float64), alphas_prev.astype(np.float64)
-    sigmas = eta * np.sqrt((1 - ap64) / (1 - a64) * (1 - a64 / ap64))
+    recip = (F32(1.0) / (F32(1.0) - alphas)).astype(np.float64)
+    sigmas = eta * np.sqrt((recip * (1 - ap64)) * (1 - a64 / ap64))
     return dict(ddim_timesteps=steps, ddim_alphas=alphas, ddim_alphas_prev=alphas_prev,
                 ddim_sigmas=sigmas.astype(F32),
                 ddim_sqrt_one_minus_alphas=np.sqrt(F32(1.0) - alphas).astype(F32),

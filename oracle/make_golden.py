@@ -1,0 +1,209 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference on CPU.  TEST INFRASTRUCTURE ONLY.
+
+    python -m oracle.make_golden            (build container only: needs /root/reference)
+
+The reference ships no golden vectors, so these outputs of the reference itself
+are what pins the oracle port (tests/test_oracle_vs_golden.py) and, through it, the CUDA path.
+Inputs are regenerated from seeds by the tests (vface_b200.synth + torch CPU generators, same torch
+build in the container and on the GPU box: the versions are recorded in every file); only outputs and
+small inputs are stored.
+"""
+from __future__ import annotations
+
+import contextlib
+import io
+import os
+import sys
+import tempfile
+
+import numpy as np
+import torch
+
+from . import ref_harness as rh
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+META = dict(torch=torch.__version__, numpy=np.__version__, reference="Sanoojan/VFace REFace/ (unmodified, CPU fp32)")
+
+SMALL_UNET = dict(model_channels=32, num_heads=2)
+
+
+def quiet():
+    return contextlib.redirect_stdout(io.StringIO())
+
+
+def save(name, **arrays):
+    os.makedirs(OUT, exist_ok=True)
+    np.savez_compressed(os.path.join(OUT, name), meta=np.array(repr(META)), **arrays)
+    print("wrote", name, {k: getattr(v, "shape", None) for k, v in arrays.items()})
+
+
+def golden_fsai():
+    from scripts.face_swap_utils import combine_fft_high_low
+    out = {}
+    for d, ratios in ((320, (0.8, 0.5, 0.25)), (640, (0.8,)), (1280, (0.8,))):
+        g = torch.Generator().manual_seed(100 + d)
+        donor = torch.randn(2, 8, d, generator=g)
+        dst = torch.randn(2, 8, d, generator=g)
+        out[f"donor_{d}"] = donor.numpy()
+        out[f"dst_{d}"] = dst.numpy()
+        for r in ratios:
+            with quiet():
+                out[f"out_{d}_{int(r * 100)}"] = combine_fft_high_low(donor, dst, split_ratio=r).numpy()
+    save("fsai.npz", **out)
+
+
+def make_flows(kind, n, hw, seed):
+    g = torch.Generator().manual_seed(seed)
+    if kind == "smooth":
+        return [torch.randn(1, 2, hw, hw, generator=g) * 3.0 for _ in range(n)]
+    if kind == "integer":
+        return [torch.randint(-5, 6, (1, 2, hw, hw), generator=g).float() for _ in range(n)]
+    return [torch.randn(1, 2, hw, hw, generator=g) * 60.0 for _ in range(n)]
+
+
+def golden_warp():
+    from scripts.temporal_flow import align_by_flow, warp_image
+    hw, c, frames = 64, 8, 3
+    out = {}
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(frames, c, hw, hw, generator=g)
+    out["x"] = x.numpy()
+    # one-hot probes: channel j of `cols` is 1 in column j, of `rows` in row j.  out[j, y, x] != 0
+    # <=> column (row) j is a bilinear tap of pixel (y, x) -- recovers the reference's floor indices.
+    cols = torch.zeros(1, hw, hw, hw)
+    rows = torch.zeros(1, hw, hw, hw)
+    for j in range(hw):
+        cols[0, j, :, j] = 1.0
+        rows[0, j, j, :] = 1.0
+    for kind in ("smooth", "integer", "far"):
+        flows = make_flows(kind, frames - 1, hw, 21)
+        out[f"flow_{kind}"] = torch.cat(flows).numpy()
+        out[f"out_{kind}"] = align_by_flow(x, flow=flows, alpha=0.8).numpy()
+        wc = warp_image(cols, flows[0])[0]           # (hw, hw, hw): [column j, y, x]
+        wr = warp_image(rows, flows[0])[0]
+        out[f"x0_{kind}"] = (wc != 0).float().argmax(dim=0).to(torch.int16).numpy()   # first tap column
+        out[f"y0_{kind}"] = (wr != 0).float().argmax(dim=0).to(torch.int16).numpy()
+        out[f"ntaps_x_{kind}"] = (wc != 0).sum(dim=0).to(torch.int16).numpy()
+        out[f"ntaps_y_{kind}"] = (wr != 0).sum(dim=0).to(torch.int16).numpy()
+    save("warp.npz", **out)
+
+
+def golden_attn_hooks():
+    """The patched attn1 forward (pnp_utils.py:92-288) on a 2-head d=40 CrossAttention, N = 4096."""
+    from ldm.modules.attention import CrossAttention
+    from ldm.models.pnp_utils import register_spa_attn_injection
+    torch.manual_seed(0)
+    attn = CrossAttention(query_dim=80, heads=2, dim_head=40)
+    g = torch.Generator().manual_seed(5)
+    for p in attn.parameters():
+        p.data = torch.randn(p.shape, generator=g) * (p.shape[-1] ** -0.5 if p.dim() > 1 else 0.02)
+
+    class Holder:                                            # model.model.model.diffusion_model.input_blocks
+        pass
+    blk = torch.nn.Module()
+    blk.attn1 = attn
+    unet = torch.nn.Module()
+    unet.input_blocks = torch.nn.ModuleList([blk])
+    unet.middle_block = torch.nn.ModuleList([])
+    unet.output_blocks = torch.nn.ModuleList([])
+    h = Holder(); h.model = Holder(); h.model.model = Holder(); h.model.model.diffusion_model = unet
+    B, N = 2, 4096
+    x = torch.randn(3 * B, N, 80, generator=g)
+    flows = make_flows("smooth", B - 1, 64, 33)
+    out = {"flow": torch.cat(flows).numpy(), "params": np.array([0])}
+    for name, p in attn.state_dict().items():
+        out["w_" + name] = p.numpy()
+    out["x_rows"] = x[:, ::32].numpy()
+    for mode, kw in (("off", dict(switch_on=False, fusion="flow_fix")),
+                     ("replace", dict(switch_on=True, fusion="replace")),
+                     ("fft", dict(switch_on=True, fusion="fft", split_ratio_fft=0.8)),
+                     ("flow_fix", dict(switch_on=True, fusion="flow_fix", split_ratio_fft=0.8, alpha=0.8, flow=flows))):
+        with quiet():
+            register_spa_attn_injection(h, 1, input_blocks=True, output_blocks=False, middle_block=False,
+                                        attn_component="attn1", chunks=3, **kw)
+            with torch.no_grad():
+                y = attn.forward(x.clone())
+        out[f"out_{mode}"] = y[:, ::32].numpy()              # every 32nd token row
+    save("attn_hooks.npz", **out)
+
+
+def golden_schedule():
+    unet = torch.nn.Identity()
+    out = {}
+    for S in (10, 50):
+        for eta in (0.0, 0.5):
+            s = rh.build_reference_sampler(unet)
+            with quiet():
+                s.make_schedule(S, ddim_eta=eta, verbose=False)
+            tag = f"S{S}_eta{int(eta * 10)}"
+            out[f"timesteps_{tag}"] = np.asarray(s.ddim_timesteps)
+            for k in ("ddim_alphas", "ddim_alphas_prev", "ddim_sigmas", "ddim_sqrt_one_minus_alphas"):
+                out[f"{k}_{tag}"] = np.asarray(torch.as_tensor(getattr(s, k)).numpy(), dtype=np.float64).astype(np.float32)
+    out["alphas_cumprod"] = rh.LatentDiffusionStub(unet).alphas_cumprod.numpy()
+    save("schedule.npz", **out)
+
+
+def golden_sampler_small():
+    from vface_b200 import synth
+    from . import kernels as ok
+    ref = rh.build_reference_unet(SMALL_UNET)
+    sd = synth.synth_state_dict(ref.state_dict(), seed=1)
+    ref.load_state_dict(sd)
+    B, S = 2, 4
+    steps = ok.make_schedule(S)["ddim_timesteps"]
+    out = {}
+    for kind in ("smooth", "integer"):
+        clip = synth.synth_clip(B, steps=steps, flow_kind=kind)
+        sampler = rh.build_reference_sampler(ref)
+        d = tempfile.mkdtemp()
+        for t, v in clip["inversion"].items():
+            torch.save(v, os.path.join(d, f"ddim_latents_{t}.pt"))
+        xs = []
+        with quiet():
+            samples, inter = sampler.sample(
+                S=S, batch_size=B, shape=(4, 64, 64), conditioning=clip["c"], target_conditioning=clip["target_cond"],
+                inverse_results_dir=d, x_T=clip["x_T"], flow=clip["flow"], unconditional_guidance_scale=3.0,
+                unconditional_conditioning=clip["uc"], eta=0.0, verbose=False, log_every_t=1,
+                test_model_kwargs=dict(inpaint_image=clip["inpaint_image"], inpaint_mask=clip["inpaint_mask"]))
+        out[f"samples_{kind}"] = samples.numpy()
+        out[f"x_inter_{kind}"] = torch.stack(inter["x_inter"][1:]).numpy()
+        out[f"pred_x0_{kind}"] = torch.stack(inter["pred_x0"][1:]).numpy()
+    # ddim_invert on the same UNet (hooks off, 2B batch, no CFG): x_T and the saved target halves
+    clip = synth.synth_clip(2 * B)
+    sampler = rh.build_reference_sampler(ref)
+    d = tempfile.mkdtemp()
+    with quiet():
+        xT, _ = sampler.ddim_invert(x=clip["x_T"], cond=clip["c"], S=S, shape=(4, 64, 64), eta=0.0, inverse_dir=d,
+                                    batch_size=B, test_model_kwargs=dict(inpaint_image=clip["inpaint_image"],
+                                                                         inpaint_mask=clip["inpaint_mask"]))
+    out["invert_xT"] = xT.numpy()
+    for t in steps:
+        out[f"invert_saved_{int(t)}"] = torch.load(os.path.join(d, f"ddim_latents_{int(t)}.pt")).numpy()
+    save("sampler_small.npz", **out)
+
+
+def golden_unet_full():
+    """One forward of the full-size UNet (project_ffhq.yaml) on a 3-way batch of one frame."""
+    from vface_b200 import synth
+    ref = rh.build_reference_unet()
+    ref.load_state_dict(synth.synth_state_dict(ref.state_dict(), seed=1))
+    clip = synth.synth_clip(1)
+    x = torch.cat([clip["x_T"], clip["inpaint_image"], clip["inpaint_mask"]], dim=1).repeat(3, 1, 1, 1)
+    x[2, :4] = torch.randn(4, 64, 64, generator=torch.Generator().manual_seed(3))
+    ctx = torch.cat([clip["uc"], clip["c"], clip["target_cond"]])
+    with torch.no_grad():
+        y = ref(x, torch.full((3,), 501, dtype=torch.long), context=ctx)
+    save("unet_full.npz", out=y.numpy(), x_recon_lat=x[2, :4].numpy())
+
+
+def main():
+    if not rh.available():
+        sys.exit("reference not mounted; golden vectors can only be generated in the build container")
+    rh.install()
+    which = sys.argv[1:] or ["fsai", "warp", "attn_hooks", "schedule", "sampler_small", "unet_full"]
+    for w in which:
+        globals()["golden_" + w]()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,188 @@
+"""Host-side logic that needs neither a GPU nor the reference: the C-ABI library's exported symbols,
+frame sharding + halo exchange over gloo (world_size 2), the sampler's schedule tables, the drop-in
+installer and the loud failure without CUDA."""
+import ctypes
+import os
+import re
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+# ---- C-ABI ------------------------------------------------------------------------------------------
+def _header_symbols():
+    src = open(os.path.join(ROOT, "include", "vface_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(vf_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from vface_b200 import _lib, build
+    build.build()                                  # no-op when fresh; nvcc cross-compiles without a GPU
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    syms = _header_symbols()
+    assert len(syms) >= 8
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in include/vface_b200.h but not exported"
+    assert set(syms) == set(_lib.SIGNATURES), "ctypes signature table out of sync with the header"
+    lib.vf_abi_version.restype = ctypes.c_int
+    assert lib.vf_abi_version() == _lib.ABI_VERSION
+
+
+def test_ops_refuse_cpu_tensors():
+    from vface_b200 import ops
+    x = torch.zeros(1, 8, 64)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ops.attention(x, x, x, 1)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ops.fsai_blend(x, x.clone())
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ops.flow_warp_blend(torch.zeros(2, 64, 8), torch.zeros(1, 2, 8, 8), 0.8, 8, 8)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ops.ddim_cfg_step(torch.zeros(4), torch.zeros(4), torch.zeros(4), 0.5, 0.6, 0.0, 0.7, 3.0)
+
+
+def test_product_does_not_import_oracle():
+    pat = re.compile(r"^\s*(from|import)\s+oracle\b|^\s*from\s+\.+\s*oracle\b", re.M)
+    for base, _, files in os.walk(os.path.join(ROOT, "vface_b200")):
+        for f in files:
+            if f.endswith(".py"):
+                assert not pat.search(open(os.path.join(base, f)).read()), f
+
+
+# ---- schedule tables ----------------------------------------------------------------------------------
+@pytest.mark.parametrize("S,eta", [(10, 0.0), (10, 0.5), (50, 0.0), (50, 0.5)])
+def test_sampler_tables_vs_reference_golden(S, eta):
+    from vface_b200.latent_diffusion import LatentDiffusion
+    from vface_b200.ldm.models.diffusion.ddim_w_inv import DDIMSampler
+    g = np.load(os.path.join(GOLD, "schedule.npz"))
+    s = DDIMSampler(LatentDiffusion(unet=torch.nn.Identity()))
+    s.make_schedule(S, ddim_eta=eta, verbose=False)
+    tag = f"S{S}_eta{int(eta * 10)}"
+    assert np.array_equal(s.ddim_timesteps, g[f"timesteps_{tag}"])
+    for k, hk in (("ddim_alphas", "a_t"), ("ddim_alphas_prev", "a_prev"), ("ddim_sigmas", "sigma"),
+                  ("ddim_sqrt_one_minus_alphas", "s1m")):
+        assert np.array_equal(s._host_tables[hk], g[f"{k}_{tag}"]), k
+    assert np.array_equal(s._host_tables["acp"], g["alphas_cumprod"])
+
+
+def test_bad_step_count_fails_like_reference():
+    """S=3 -> range(0,1000,333)+1 reaches 1000 -> IndexError in the reference."""
+    from vface_b200.latent_diffusion import LatentDiffusion
+    from vface_b200.ldm.models.diffusion.ddim_w_inv import DDIMSampler
+    s = DDIMSampler(LatentDiffusion(unet=torch.nn.Identity()))
+    with pytest.raises(IndexError):
+        s.make_schedule(3, verbose=False)
+
+
+# ---- hooks registration (plugin mechanism) --------------------------------------------------------------
+def test_hook_registration_census():
+    """input 6 / middle 1 / output 9 attn1 modules; instance-level forward patching."""
+    from vface_b200.latent_diffusion import LatentDiffusion
+    from vface_b200.ldm.models.diffusion.ddim_w_inv import DDIMSampler
+    from vface_b200.ldm.models.pnp_utils import find_all_modules_by_name, register_spa_attn_injection
+    model = LatentDiffusion(unet_config=dict(model_channels=32, num_heads=2))
+    unet = model.model.diffusion_model
+    census = [len(find_all_modules_by_name(b, "attn1")[0]) for b in (unet.input_blocks, unet.middle_block, unet.output_blocks)]
+    assert census == [6, 1, 9]
+    names = find_all_modules_by_name(unet.input_blocks, "attn1")[1]
+    assert names == [f"{i}.1.transformer_blocks.0.attn1" for i in (1, 2, 4, 5, 7, 8)]
+    s = DDIMSampler(model)
+    s._register_hooks(flow=None)
+    for blocks, n in ((unet.input_blocks, 6), (unet.middle_block, 1), (unet.output_blocks, 9)):
+        mods = find_all_modules_by_name(blocks, "attn1")[0]
+        assert sum("forward" in m.__dict__ for m in mods) == n
+    with pytest.raises(NotImplementedError):
+        register_spa_attn_injection(s, 1, fusion="adaIn")
+    # block_indices filter: the others only get the schedule attribute, like the reference
+    model2 = LatentDiffusion(unet_config=dict(model_channels=32, num_heads=2))
+    s2 = DDIMSampler(model2)
+    register_spa_attn_injection(s2, 7, input_blocks=True, output_blocks=False, block_indices=[0, 2], fusion="fft")
+    mods = find_all_modules_by_name(model2.model.diffusion_model.input_blocks, "attn1")[0]
+    assert ["forward" in m.__dict__ for m in mods] == [True, False, True, False, False, False]
+    assert mods[1].injection_schedule == 7
+
+
+def test_install_rebinds_reference_modules():
+    import types
+    import vface_b200
+    fake = {}
+    for name in ("ldm", "ldm.models", "ldm.models.diffusion", "ldm.models.diffusion.ddim_w_inv", "ldm.models.pnp_utils"):
+        if name in sys.modules:
+            pytest.skip("a real ldm package is already imported in this process")
+    try:
+        for name in ("ldm", "ldm.models", "ldm.models.diffusion", "ldm.models.diffusion.ddim_w_inv", "ldm.models.pnp_utils"):
+            fake[name] = sys.modules[name] = types.ModuleType(name)
+        done = vface_b200.install()
+        from vface_b200.ldm.models.diffusion.ddim_w_inv import DDIMSampler
+        assert fake["ldm.models.diffusion.ddim_w_inv"].DDIMSampler is DDIMSampler
+        assert ("ldm.models.pnp_utils", "register_spa_attn_injection") in done
+    finally:
+        for name in fake:
+            sys.modules.pop(name, None)
+
+
+# ---- frame sharding ---------------------------------------------------------------------------------
+def test_shard_bounds_bit_exact():
+    from vface_b200.frame_shard import shard_bounds
+    assert shard_bounds(256, 8) == [(32 * r, 32 * (r + 1)) for r in range(8)]
+    assert shard_bounds(256, 2) == [(0, 128), (128, 256)]
+    assert shard_bounds(10, 4) == [(0, 2), (2, 5), (5, 7), (7, 10)]
+    for f, g in ((256, 8), (33, 4), (7, 7)):
+        b = shard_bounds(f, g)
+        assert b[0][0] == 0 and b[-1][1] == f and all(b[i][1] == b[i + 1][0] for i in range(g - 1))
+    with pytest.raises(ValueError):
+        shard_bounds(3, 4)
+
+
+def _halo_worker(rank, world, port, frames_total, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle import kernels as ok
+        from vface_b200.frame_shard import FrameShard
+        h = w = 16
+        c = 8
+        g = torch.Generator().manual_seed(0)
+        x = torch.randn(frames_total, h * w, c, generator=g)
+        flow = torch.randn(frames_total - 1, 2, h, w, generator=g) * 2
+        full = ok.flow_warp_blend(x.numpy(), flow.numpy(), 0.8, h, w)
+        sh = FrameShard(rank, world, frames_total)
+        xl = sh.take(x)
+        fl = sh.local_flow(flow)
+        halo_q, halo_k = sh.exchange_halo(xl[-1], -xl[-1])
+        if rank == 0:
+            assert halo_q is None and len(fl) == sh.frames - 1
+            loc = ok.flow_warp_blend(xl.numpy(), fl.numpy(), 0.8, h, w)
+        else:
+            assert torch.equal(halo_q, x[sh.lo - 1]) and torch.equal(halo_k, -x[sh.lo - 1])
+            assert len(fl) == sh.frames
+            loc = ok.flow_warp_blend(xl.numpy(), fl.numpy(), 0.8, h, w, prev_halo=halo_q.numpy())
+        assert np.array_equal(loc, full[sh.lo:sh.hi])                 # sharded == unsharded, bit-exact
+        gathered = sh.gather_frames(torch.from_numpy(loc))
+        assert np.array_equal(gathered.numpy(), full)
+        assert sh.halo_messages == (1 if rank + 1 < world else 0)
+        ret[rank] = True
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,frames", [(2, 6), (2, 7), (3, 8)])
+def test_halo_exchange_gloo(world, frames):
+    import socket
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_halo_worker, args=(world, port, frames, ret), nprocs=world, join=True)
+    assert all(ret.get(r) for r in range(world))

@@ -1,0 +1,234 @@
+"""The REFace / Paint-by-Example denoising UNet on the vface_b200 kernels.
+
+Host-side mirror of REFace/ldm/modules/diffusionmodules/openaimodel.py: UNetModel :528-907,
+ResBlock :163-275, Upsample :91-119, Downsample :134-160, TimestepEmbedSequential :74-88.
+Constructor keywords are the reference's (models/REFace/configs/project_ffhq.yaml:33-55) and the
+module tree -- hence every state-dict key -- is identical, so the reference checkpoint loads as is.
+
+What differs is the execution plan: activations are channels_last (NHWC) in the parameter dtype
+(bf16 on the throughput path), so the 16 SpatialTransformers see their (b, hw, c) token view
+without a copy, attention never materialises N x N, and gradient checkpointing (a training device,
+`use_checkpoint`) is a no-op.  Convolutions, GroupNorm and the projection GEMMs stay on
+cuDNN/cuBLAS (outside the four hand-written subsystems).
+
+Options of the reference constructor that the VFace configuration never enables raise
+NotImplementedError instead of being silently ignored.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from ..attention import SpatialTransformer
+from .util import normalization, timestep_embedding, zero_module
+
+
+class TimestepBlock(nn.Module):
+    """Marker: forward(x, emb)."""
+
+
+class TimestepEmbedSequential(nn.Sequential, TimestepBlock):
+    def forward(self, x, emb, context=None):
+        for layer in self:
+            if isinstance(layer, TimestepBlock):
+                x = layer(x, emb)
+            elif isinstance(layer, SpatialTransformer):
+                x = layer(x, context)
+            else:
+                x = layer(x)
+        return x
+
+
+class Upsample(nn.Module):
+    def __init__(self, channels, use_conv, dims=2, out_channels=None, padding=1):
+        super().__init__()
+        self.channels = channels
+        self.out_channels = out_channels or channels
+        self.use_conv = use_conv
+        self.dims = dims
+        if use_conv:
+            self.conv = nn.Conv2d(self.channels, self.out_channels, 3, padding=padding)
+
+    def forward(self, x):
+        x = F.interpolate(x, scale_factor=2, mode="nearest")
+        return self.conv(x) if self.use_conv else x
+
+
+class Downsample(nn.Module):
+    def __init__(self, channels, use_conv, dims=2, out_channels=None, padding=1):
+        super().__init__()
+        self.channels = channels
+        self.out_channels = out_channels or channels
+        self.use_conv = use_conv
+        self.dims = dims
+        if use_conv:
+            self.op = nn.Conv2d(self.channels, self.out_channels, 3, stride=2, padding=padding)
+        else:
+            self.op = nn.AvgPool2d(kernel_size=2, stride=2)
+
+    def forward(self, x):
+        return self.op(x)
+
+
+class ResBlock(TimestepBlock):
+    """GN-SiLU-conv3x3, + emb projection, GN-SiLU-(dropout)-conv3x3 (zero-init), + skip."""
+
+    def __init__(self, channels, emb_channels, dropout, out_channels=None, use_conv=False,
+                 use_scale_shift_norm=False, dims=2, use_checkpoint=False, up=False, down=False):
+        super().__init__()
+        if up or down or use_scale_shift_norm or dims != 2:
+            raise NotImplementedError("resblock_updown / scale-shift norm / non-2D are not used by the VFace configuration")
+        self.channels = channels
+        self.emb_channels = emb_channels
+        self.dropout = dropout
+        self.out_channels = out_channels or channels
+        self.use_conv = use_conv
+        self.use_checkpoint = use_checkpoint
+        self.use_scale_shift_norm = use_scale_shift_norm
+        self.updown = False
+        self.in_layers = nn.Sequential(normalization(channels), nn.SiLU(),
+                                       nn.Conv2d(channels, self.out_channels, 3, padding=1))
+        self.h_upd = self.x_upd = nn.Identity()
+        self.emb_layers = nn.Sequential(nn.SiLU(), nn.Linear(emb_channels, self.out_channels))
+        self.out_layers = nn.Sequential(normalization(self.out_channels), nn.SiLU(), nn.Dropout(p=dropout),
+                                        zero_module(nn.Conv2d(self.out_channels, self.out_channels, 3, padding=1)))
+        if self.out_channels == channels:
+            self.skip_connection = nn.Identity()
+        elif use_conv:
+            self.skip_connection = nn.Conv2d(channels, self.out_channels, 3, padding=1)
+        else:
+            self.skip_connection = nn.Conv2d(channels, self.out_channels, 1)
+
+    def forward(self, x, emb):
+        return self._forward(x, emb)
+
+    def _forward(self, x, emb):
+        h = self.in_layers(x)
+        emb_out = self.emb_layers(emb).type(h.dtype)
+        h = h + emb_out[:, :, None, None]
+        h = self.out_layers(h)
+        return self.skip_connection(x) + h
+
+
+class UNetModel(nn.Module):
+    def __init__(self, image_size, in_channels, model_channels, out_channels, num_res_blocks,
+                 attention_resolutions, dropout=0, channel_mult=(1, 2, 4, 8), conv_resample=True, dims=2,
+                 num_classes=None, use_checkpoint=False, use_fp16=False, num_heads=-1, num_head_channels=-1,
+                 num_heads_upsample=-1, use_scale_shift_norm=False, resblock_updown=False,
+                 use_new_attention_order=False, use_spatial_transformer=False, transformer_depth=1,
+                 context_dim=None, n_embed=None, legacy=True, add_conv_in_front_of_unet=False,
+                 sep_head_att=False, land_mark_id_seperate_layers=False, head_splits=None):
+        super().__init__()
+        unsupported = dict(dims=dims != 2, num_classes=num_classes is not None, n_embed=n_embed is not None,
+                           use_scale_shift_norm=use_scale_shift_norm, resblock_updown=resblock_updown,
+                           add_conv_in_front_of_unet=add_conv_in_front_of_unet, sep_head_att=sep_head_att,
+                           land_mark_id_seperate_layers=land_mark_id_seperate_layers,
+                           no_spatial_transformer=not use_spatial_transformer)
+        bad = [k for k, v in unsupported.items() if v]
+        if bad:
+            raise NotImplementedError(f"UNetModel options outside the VFace configuration: {bad}")
+        if context_dim is None:
+            raise ValueError("use_spatial_transformer needs context_dim")
+        if num_heads == -1 and num_head_channels == -1:
+            raise ValueError("either num_heads or num_head_channels has to be set")
+        if not isinstance(context_dim, int):
+            context_dim = list(context_dim)   # OmegaConf ListConfig
+            raise NotImplementedError("list-valued context_dim is not used by the VFace configuration")
+        if num_heads_upsample == -1:
+            num_heads_upsample = num_heads
+
+        self.image_size = image_size
+        self.in_channels = in_channels
+        self.model_channels = model_channels
+        self.out_channels = out_channels
+        self.num_res_blocks = num_res_blocks
+        self.attention_resolutions = list(attention_resolutions)
+        self.dropout = dropout
+        self.channel_mult = list(channel_mult)
+        self.conv_resample = conv_resample
+        self.num_classes = None
+        self.use_checkpoint = use_checkpoint
+        self.num_heads = num_heads
+        self.num_head_channels = num_head_channels
+        self.num_heads_upsample = num_heads_upsample
+        self.predict_codebook_ids = False
+
+        def heads_for(ch):
+            if num_head_channels == -1:
+                return num_heads, ch // num_heads
+            return ch // num_head_channels, num_head_channels
+
+        def transformer(ch):
+            nh, dh = heads_for(ch)
+            return SpatialTransformer(ch, nh, dh, depth=transformer_depth, context_dim=context_dim)
+
+        def res(cin, cout):
+            return ResBlock(cin, time_embed_dim, dropout, out_channels=cout, use_checkpoint=use_checkpoint)
+
+        time_embed_dim = model_channels * 4
+        self.time_embed = nn.Sequential(nn.Linear(model_channels, time_embed_dim), nn.SiLU(),
+                                        nn.Linear(time_embed_dim, time_embed_dim))
+
+        # ---- encoder ----------------------------------------------------------------------------
+        self.input_blocks = nn.ModuleList(
+            [TimestepEmbedSequential(nn.Conv2d(in_channels, model_channels, 3, padding=1))])
+        skip_chans = [model_channels]
+        ch, ds = model_channels, 1
+        for level, mult in enumerate(self.channel_mult):
+            for _ in range(num_res_blocks):
+                layers = [res(ch, mult * model_channels)]
+                ch = mult * model_channels
+                if ds in self.attention_resolutions:
+                    layers.append(transformer(ch))
+                self.input_blocks.append(TimestepEmbedSequential(*layers))
+                skip_chans.append(ch)
+            if level != len(self.channel_mult) - 1:
+                self.input_blocks.append(TimestepEmbedSequential(Downsample(ch, conv_resample, out_channels=ch)))
+                skip_chans.append(ch)
+                ds *= 2
+
+        # ---- bottleneck -------------------------------------------------------------------------
+        self.middle_block = TimestepEmbedSequential(res(ch, ch), transformer(ch), res(ch, ch))
+
+        # ---- decoder ----------------------------------------------------------------------------
+        self.output_blocks = nn.ModuleList([])
+        for level, mult in list(enumerate(self.channel_mult))[::-1]:
+            for i in range(num_res_blocks + 1):
+                layers = [res(ch + skip_chans.pop(), model_channels * mult)]
+                ch = model_channels * mult
+                if ds in self.attention_resolutions:
+                    layers.append(transformer(ch))
+                if level and i == num_res_blocks:
+                    layers.append(Upsample(ch, conv_resample, out_channels=ch))
+                    ds //= 2
+                self.output_blocks.append(TimestepEmbedSequential(*layers))
+
+        self.out = nn.Sequential(normalization(ch), nn.SiLU(),
+                                 zero_module(nn.Conv2d(model_channels, out_channels, 3, padding=1)))
+
+    @property
+    def dtype(self):
+        return self.input_blocks[0][0].weight.dtype
+
+    def forward(self, x, timesteps=None, context=None, y=None, return_features=False, **kwargs):
+        """(N, in_channels, H, W), (N,) timesteps, (N, M, context_dim) -> (N, out_channels, H, W)."""
+        if y is not None:
+            raise NotImplementedError("class-conditional UNet is not used by the VFace configuration")
+        dt = self.dtype
+        emb = self.time_embed(timestep_embedding(timesteps, self.model_channels).to(dt))
+        context = context.to(dt)
+        h = x.to(dt).contiguous(memory_format=torch.channels_last)
+        hs = []
+        for module in self.input_blocks:
+            h = module(h, emb, context)
+            hs.append(h)
+        h = self.middle_block(h, emb, context)
+        features = []
+        for module in self.output_blocks:
+            h = torch.cat([h, hs.pop()], dim=1)
+            h = module(h, emb, context)
+            if return_features:
+                features.append(h)
+        out = self.out(h).to(x.dtype).contiguous()
+        return (out, features) if return_features else out

@@ -45,7 +45,11 @@ def make_ddim_sampling_parameters(alphacums, ddim_timesteps, eta, verbose=True):
     alphas = acp[torch.as_tensor(ddim_timesteps, dtype=torch.long)]
     alphas_prev = np.asarray([acp[0].item()] + acp[torch.as_tensor(ddim_timesteps[:-1], dtype=torch.long)].tolist())
     a64 = alphas.double().numpy()
-    sigmas = eta * np.sqrt((1 - alphas_prev) / (1 - a64) * (1 - a64 / alphas_prev))
+    # The reference evaluates this with a fp32 tensor (alphas) and a fp64 array (alphas_prev); numpy
+    # defers `array / tensor` to Tensor.__rtruediv__ = reciprocal(tensor) * array, so 1/(1 - alphas)
+    # is rounded to fp32 and every other term is fp64.  Reproduced so sigma_t is bit-identical (eta > 0).
+    recip = (1. - alphas).reciprocal().double().numpy()
+    sigmas = eta * np.sqrt((recip * (1 - alphas_prev)) * (1 - a64 / alphas_prev))
     if verbose:
         print(f"Selected alphas for ddim sampler: a_t: {alphas}; a_(t-1): {alphas_prev}")
         print(f"For the chosen value of eta, which is {eta}, this results in the following sigma_t schedule "
