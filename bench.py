@@ -1,0 +1,386 @@
+#!/usr/bin/env python
+"""Headline benchmark of the VFace denoising hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--frames F] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+
+Workload (BASELINE.json configs[1]): full VFace pipeline, 32-frame 512x512 clip per GPU, DDIM-50 with
+CFG 3.0, bf16 kernels, random-init weights of the named UNet (859.5 M parameters, every zero-module
+re-randomised) and synthetic clips -- no checkpoints or datasets exist offline.
+
+  step      one denoising step (DDIMSampler.p_sample_ddim_with_inverse: 3-way UNet batch with the
+            VFace hooks on + fused CFG/DDIM update) over the rank's 32 frames; consecutive timed steps
+            walk down the DDIM-50 schedule.
+  value     frames/s at DDIM-50 = total frames / (50 * step time); inputs resident in HBM.
+  e2e       the same metric through the public API, DDIMSampler.sample(S=50) on HOST (pinned)
+            buffers: all host->device copies (clip, conditioning, flow, 50 inversion latents) and the
+            device->host read of the samples are inside the timed region.
+  roofline  the dominant kernel (fused tcgen05 attention at N=4096, 8 heads x d40), timed live with
+            CUDA events around every launch inside the timed steps.
+  N > 1     frames shard by contiguous chunk (weak scaling: 32 frames per GPU, so N=8 is the 256-frame
+            clip); the only exchange is the one-frame q/k halo per flow-active module per step.
+
+--impl reference times the reference's CPU path (oracle port, kind "port": the reference is Python and
+cannot travel to the GPU box) on the host cores, on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+DDIM_STEPS = 50
+CFG_SCALE = 3.0
+METRIC = "frames/s at 512^2 DDIM-50 (VFace denoising hot path)"
+UNIT = "frames/s"
+# attn1 modules at N=4096 (64x64, 8 heads x d40): input_blocks.1/.2, output_blocks.9/.10/.11
+ATTN4096_FLOPS_PER_SAMPLE = 4.0 * 4096 * 4096 * 40 * 8
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tc_burst=d["bf16_tflops"], tc_sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]), src="measured")
+    return dict(hbm=6650.0, tc_burst=1590.0, tc_sustained=1400.0, src="fallback")
+
+
+# ---- clocks -----------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting", 0x10: "sync_boost"}
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if not self.ok:
+            return
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                try:
+                    mask = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    mask = self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.05)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        med = float(np.median(self.samples)) if self.samples else None
+        return dict(sm_mhz=med, sm_max_mhz=self.max_mhz, reasons=sorted(self.reasons), samples=len(self.samples))
+
+
+def physical_gpu_index(local):
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    if vis:
+        try:
+            return int(vis.split(",")[local])
+        except Exception:
+            return local
+    return local
+
+
+# ---- model / clip ---------------------------------------------------------------------------------------
+def build_model(device, dtype, state=None):
+    from vface_b200 import synth
+    from vface_b200.latent_diffusion import LatentDiffusion
+    model = LatentDiffusion()
+    unet = model.model.diffusion_model
+    sd = state if state is not None else synth.synth_state_dict(unet.state_dict(), seed=1)
+    unet.load_state_dict(sd)
+    model = model.to(device).eval()
+    unet.to(dtype)
+    return model, sd
+
+
+def local_clip(frames, rank, steps):
+    from vface_b200 import synth
+    clip = synth.synth_clip(frames + (1 if rank > 0 else 0), seed=7 + 101 * rank, steps=steps)
+    if rank > 0:
+        # one extra leading flow field (halo frame -> first local frame); per-frame tensors drop the extra frame
+        for k in ("x_T", "inpaint_image", "inpaint_mask", "c", "target_cond", "uc"):
+            clip[k] = clip[k][1:].contiguous()
+        clip["inversion"] = {t: v[1:].contiguous() for t, v in clip["inversion"].items()}
+    return clip
+
+
+# ---- CPU baseline (oracle port) -------------------------------------------------------------------------------
+def cpu_step_seconds(sd, frames, warm, reps):
+    """Seconds per denoising step of the reference path on the host cores (oracle port), `frames` frames."""
+    from oracle import kernels as ok, port
+    from vface_b200 import synth
+    steps = ok.make_schedule(DDIM_STEPS)["ddim_timesteps"]
+    clip = synth.synth_clip(max(frames, 2), steps=steps[-(warm + reps):])
+    take = lambda t: t[:frames]
+    ts = []
+    hooks = port.vface_hooks(sd, clip["flow"][:frames - 1] if frames > 1 else None)
+    extra = torch.cat([take(clip["inpaint_image"]), take(clip["inpaint_mask"])], dim=1)
+    x = take(clip["x_T"])
+    for i, step in enumerate(np.flip(steps)[:warm + reps]):
+        t0 = time.perf_counter()
+        tt = torch.full((frames,), int(step), dtype=torch.long)
+        x_full = torch.cat([x, extra], dim=1)
+        inv_full = torch.cat([take(clip["inversion"][int(step)]), extra], dim=1)
+        x_in = torch.cat([x_full, x_full, inv_full])
+        c_in = torch.cat([take(clip["uc"]), take(clip["c"]), take(clip["target_cond"])])
+        with torch.no_grad():
+            e_u, e_c, _ = port.unet_forward(sd, x_in, torch.cat([tt] * 3), c_in, 8, hooks).chunk(3)
+        tb = ok.make_schedule(DDIM_STEPS)
+        idx = DDIM_STEPS - 1 - i
+        xp, _ = ok.ddim_cfg_step(x.numpy(), e_u.numpy(), e_c.numpy(), tb["ddim_alphas"][idx], tb["ddim_alphas_prev"][idx],
+                                 tb["ddim_sigmas"][idx], tb["ddim_sqrt_one_minus_alphas"][idx], CFG_SCALE)
+        x = torch.from_numpy(xp)
+        ts.append(time.perf_counter() - t0)
+    return float(np.mean(ts[warm:])), ts
+
+
+def run_reference_arm(args, rank):
+    if rank != 0:
+        return
+    from vface_b200 import synth
+    from vface_b200.latent_diffusion import LatentDiffusion
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = synth.synth_state_dict(LatentDiffusion().model.diffusion_model.state_dict(), seed=1)
+    frames = 1
+    # bounded: one frame per step; at most ~5 minutes in total
+    t_probe, _ = cpu_step_seconds(sd, frames, 0, 1)
+    budget = 300.0
+    K, W = args.steps, args.warmup
+    fit = max(1, int(budget / max(t_probe, 1e-3)) - 1)
+    note = None
+    if W + K > fit:
+        W = min(W, max(0, fit // 4))
+        K2 = max(1, fit - W)
+        if K2 < K:
+            note = f"steps reduced from {K} to {K2} to bound the CPU run to ~{int(budget)} s"
+            K = K2
+    t_step, _ = cpu_step_seconds(sd, frames, W, K)
+    value = frames / (DDIM_STEPS * t_step)
+    sample = (f"{frames} frame(s) per step (UNet batch {3 * frames}, hooks on), {K} timed DDIM steps of the same "
+              f"full-size UNet; fp32 PyTorch on {cores} host threads")
+    line = dict(impl="reference", metric=METRIC, value=value, unit=UNIT, n_gpus=args.gpus, steps=K, warmup=W,
+                ms_per_step=t_step * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
+                data="synthetic",
+                config=dict(workload="VFace full pipeline, 32-frame 512x512 clip per GPU, DDIM-50, CFG 3.0 "
+                                     "(reference CPU path measured on a bounded 1-frame sample)",
+                            frames_per_step=frames, ddim_steps=DDIM_STEPS, cfg_scale=CFG_SCALE),
+                cpu_baseline=dict(value=value, unit=UNIT, cores=cores, kind="port", sample=sample),
+                e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    if note:
+        line["note"] = note
+    print(json.dumps(line), flush=True)
+
+
+# ---- main arm ---------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--frames", type=int, default=32, help="frames per GPU")
+    ap.add_argument("--impl", default="vface_b200")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--elide-recon", action="store_true", help="skip the output-dead recon branch (SURVEY.md F3)")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference_arm(args, rank)
+        return
+
+    import torch.distributed as dist
+    from vface_b200 import frame_shard, ops
+    from vface_b200.ldm.models.diffusion.ddim_w_inv import DDIMSampler
+
+    if not torch.cuda.is_available():
+        sys.exit("bench.py needs a CUDA device: vface_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=device)
+    W = max(args.warmup, 3)
+    K = max(args.steps, 1)
+    frames = args.frames
+    total_frames = frames * world
+
+    model, sd = build_model(device, torch.bfloat16)
+    sampler = DDIMSampler(model, elide_dead_recon=args.elide_recon)
+    sampler.make_schedule(DDIM_STEPS, ddim_eta=0.0, verbose=False)
+    steps = sampler.ddim_timesteps
+    shard = frame_shard.FrameShard(rank, world, total_frames)
+    frame_shard.activate(shard)
+
+    clip = local_clip(frames, rank, steps)
+    pin = lambda t: t.pin_memory()
+    host = {k: pin(v) for k, v in clip.items() if isinstance(v, torch.Tensor)}
+    host_flow = pin(torch.cat(clip["flow"], dim=0))
+    host_inv = {t: pin(v) for t, v in clip["inversion"].items()}
+    dev = {k: v.to(device) for k, v in host.items()}
+    dev_flow = host_flow.to(device)
+    dev_inv = {t: v.to(device) for t, v in host_inv.items()}
+    kw = dict(test_model_kwargs=dict(inpaint_image=dev["inpaint_image"], inpaint_mask=dev["inpaint_mask"]))
+    sampler._register_hooks(dev_flow)
+    sampler._inv_cache = dev_inv
+    time_range = np.flip(steps)
+
+    def one_step(i, x):
+        i = i % DDIM_STEPS
+        step = int(time_range[i])
+        ts = torch.full((frames,), step, device=device, dtype=torch.long)
+        x_prev, _ = sampler.p_sample_ddim_with_inverse(
+            x, dev["c"], ts, index=DDIM_STEPS - 1 - i, target_conditioning=dev["target_cond"],
+            inverse_results_dir=dev_inv, unconditional_guidance_scale=CFG_SCALE,
+            unconditional_conditioning=dev["uc"], flow=dev_flow, _step=step, **kw)
+        return x_prev
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    x = dev["x_T"]
+    with torch.no_grad():
+        for i in range(W):
+            x = one_step(i, x)
+        barrier()
+        clocks = ClockSampler(physical_gpu_index(local_rank))
+        clocks.start()
+        ops.profile_attention(min_tokens=4096)
+        launches0 = ops.launch_count
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for i in range(W, W + K):
+            x = one_step(i, x)
+        ev1.record()
+        barrier()
+        clock_info = clocks.stop()
+        launches = ops.launch_count - launches0
+        attn_ms = ops.profile_attention(None)
+    ms_total = ev0.elapsed_time(ev1)
+    tmax = torch.tensor([ms_total], device=device, dtype=torch.float64)
+    lsum = torch.tensor([float(launches)], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(lsum, op=dist.ReduceOp.SUM)
+    ms_per_step = tmax.item() / K
+    value = total_frames / (DDIM_STEPS * ms_per_step * 1e-3)
+
+    # ---- roofline of the dominant kernel (fused attention, N=4096) -------------------------------------
+    pk = peaks()
+    n_branches = 2 if args.elide_recon else 3
+    roof = None
+    if attn_ms:
+        avg_ms = float(np.mean(attn_ms))
+        flops = ATTN4096_FLOPS_PER_SAMPLE * frames * n_branches
+        ach = flops / (avg_ms * 1e-3) / 1e12
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "attn_traffic.json")
+        if os.path.exists(tp):
+            try:
+                traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        roof = dict(bound="tensor", kernel="attn_tc_kernel<128,256> (N=4096, 8 heads x d40)", achieved=ach,
+                    peak=pk["tc_sustained"], unit="TFLOP/s", frac=ach / pk["tc_sustained"], traffic=traffic,
+                    peak_source=f"{pk['src']} sustained bf16 (kernel timed inside a long step); burst {pk['tc_burst']}",
+                    frac_of_burst=ach / pk["tc_burst"], launches_timed=len(attn_ms), avg_launch_ms=avg_ms,
+                    share_of_step=float(np.sum(attn_ms)) / K / ms_per_step,
+                    algorithmic_flops_per_launch=flops)
+
+    # ---- end to end through the public API, host buffers ------------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        h2d = sum(v.numel() * v.element_size() for v in host.values()) + host_flow.numel() * 4 \
+            + sum(v.numel() * 4 for v in host_inv.values())
+        d2h = frames * 4 * 64 * 64 * 4
+        out_host = torch.empty(frames, 4, 64, 64).pin_memory()
+
+        def sample_e2e():
+            g = lambda t: t.to(device, non_blocking=True)
+            inv = {t: g(v) for t, v in host_inv.items()}
+            samples, _ = sampler.sample(
+                S=DDIM_STEPS, batch_size=frames, shape=(4, 64, 64), conditioning=g(host["c"]),
+                target_conditioning=g(host["target_cond"]), inverse_results_dir=inv, x_T=g(host["x_T"]),
+                flow=g(host_flow), unconditional_guidance_scale=CFG_SCALE, unconditional_conditioning=g(host["uc"]),
+                eta=0.0, verbose=False,
+                test_model_kwargs=dict(inpaint_image=g(host["inpaint_image"]), inpaint_mask=g(host["inpaint_mask"])))
+            out_host.copy_(samples, non_blocking=True)
+            torch.cuda.synchronize()
+            return out_host
+
+        barrier()
+        t0 = time.perf_counter()
+        sample_e2e()
+        barrier()
+        t_e2e = time.perf_counter() - t0
+        te = torch.tensor([t_e2e], device=device, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e = dict(value=total_frames / te.item(), unit=UNIT, h2d_bytes_per_step=int(h2d // DDIM_STEPS),
+                   d2h_bytes_per_step=int(d2h // DDIM_STEPS), seconds=te.item(),
+                   call="DDIMSampler.sample(S=50, ...) on pinned host buffers, one full DDIM-50 pass")
+
+    # ---- CPU baseline beside it (rank 0, N=1 only) -----------------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        sd32 = {k: v.float() for k, v in sd.items()}
+        t_step, _ = cpu_step_seconds(sd32, 1, 0, 1)
+        cpu = dict(value=1.0 / (DDIM_STEPS * t_step), unit=UNIT, cores=cores, kind="port",
+                   sample="1 frame x 1 DDIM step (UNet batch 3, hooks on) of the same full-size UNet, fp32 PyTorch "
+                          f"on {cores} host threads; {t_step:.1f} s")
+
+    if rank == 0:
+        line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=K, warmup=W, ms_per_step=ms_per_step,
+                    higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16", data="synthetic",
+                    config=dict(workload="VFace full pipeline, 32-frame 512x512 clip per GPU, DDIM-50 with CFG 3.0, bf16",
+                                frames_per_gpu=frames, total_frames=total_frames, ddim_steps=DDIM_STEPS, cfg_scale=CFG_SCALE,
+                                unet_batch_per_step=n_branches * frames, branches=n_branches, parallelism=f"frame-shard x{world}",
+                                l2="step working set (1.7 GB weights + activations) far exceeds the 126 MB L2; no flush needed",
+                                weights="random-init REFace UNet 859.5M params, zero-modules re-randomised (seed 1)"),
+                    clocks=clock_info, e2e=e2e, gpu_launches=int(lsum.item()), roofline=roof, cpu_baseline=cpu,
+                    halo=dict(messages=shard.halo_messages, bytes=shard.halo_bytes) if world > 1 else None)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

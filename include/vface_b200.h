@@ -28,7 +28,7 @@ extern "C" {
 #define VF_F32 0
 #define VF_BF16 1
 
-#define VF_ABI_VERSION 1
+#define VF_ABI_VERSION 2
 
 /* ABI version of the loaded library (== VF_ABI_VERSION). */
 int vf_abi_version(void);
@@ -124,6 +124,48 @@ int vf_ddim_cfg_step(const void* x, const void* e_uncond, const void* e_cond,
 int vf_ddim_invert_step(const void* x, const void* e_uncond, const void* e_cond, void* x_next,
                         float a_cur, float a_next, float cfg_scale,
                         long long n, int dtype_e, void* stream);
+
+/*
+ * ---- fused glue kernels of the UNet between its GEMM-shaped ops ----------
+ * All take channels-last / token-major activations: rows of `c` contiguous channels.
+ */
+
+/*
+ * GroupNorm32 on channels-last activations x: (n, hw, c), fp32 statistics:
+ *   y = act( GN(x + add_nc[n, :]) * gamma + beta ),  act = SiLU if silu != 0.
+ * Replaces normalization() -> SiLU at ldm/modules/diffusionmodules/openaimodel.py:201-205, :236-239
+ * (GroupNorm32, util.py:214-216), the `h + emb_out` add of ResBlock._forward (:265-273, through
+ * add_nc, which may be NULL) and Normalize() of SpatialTransformer (attention.py:278-281).
+ * workspace: vf_group_norm_workspace_floats(n, hw, groups) floats of device scratch.
+ */
+long long vf_group_norm_workspace_floats(int n, int hw, int groups);
+int vf_group_norm_nhwc(const void* x, const void* add_nc, const void* gamma, const void* beta, void* y,
+                       float* workspace, int n, int hw, int c, int groups, float eps, int silu,
+                       int dtype, void* stream);
+
+/*
+ * res = x + y + bias ; out = LayerNorm(res) * gamma + beta over the last axis (c).
+ * y and bias may be NULL (then res may be NULL and out = LayerNorm(x)).  bias is (rows/rows_per_bias, c)
+ * when rows_per_bias > 0 (one row per sample) or a single (c) row when rows_per_bias == 0.
+ * Replaces `attn(norm(x)) + x` followed by the next nn.LayerNorm in
+ * BasicTransformerBlock._forward (ldm/modules/attention.py:239-243).
+ */
+int vf_add_layer_norm(const void* x, const void* y, const void* bias, long long rows_per_bias,
+                      const void* gamma, const void* beta, void* res, void* out,
+                      long long rows, int c, float eps, int dtype, void* stream);
+
+/*
+ * GEGLU gate: out[r, 0:k] = h[r, 0:k] * gelu(h[r, k:2k]) (exact erf GELU); h row stride ld_h >= 2k.
+ * Replaces GEGLU.forward (ldm/modules/attention.py:43-45).
+ */
+int vf_geglu(const void* h, void* out, long long rows, int k, long long ld_h, int dtype, void* stream);
+
+/*
+ * out = a + b + bias (b, bias optional; bias rows as in vf_add_layer_norm).  Residual adds and the
+ * convolution biases of ResBlock / SpatialTransformer (openaimodel.py:275, attention.py:288).
+ */
+int vf_add_bias(const void* a, const void* b, const void* bias, long long rows_per_bias, void* out,
+                long long rows, int c, int dtype, void* stream);
 
 #ifdef __cplusplus
 }

@@ -149,7 +149,7 @@ def golden_sampler_small():
     ref = rh.build_reference_unet(SMALL_UNET)
     sd = synth.synth_state_dict(ref.state_dict(), seed=1)
     ref.load_state_dict(sd)
-    B, S = 2, 4
+    B, S = 2, 10         # BASELINE.json config 1: DDIM 10 steps
     steps = ok.make_schedule(S)["ddim_timesteps"]
     out = {}
     for kind in ("smooth", "integer"):

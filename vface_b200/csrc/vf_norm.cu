@@ -1,0 +1,457 @@
+// Fused memory-bound glue kernels of the UNet between the GEMM-shaped ops:
+//
+//   vf_group_norm_nhwc   GroupNorm32 (+ per-(sample,channel) additive vector, + SiLU) on channels-last
+//                        activations; replaces GroupNorm32 -> SiLU (openaimodel.py:201-205, :236-239,
+//                        util.py:214-216) and the `h + emb_out` add of ResBlock._forward (:265-273).
+//   vf_add_layer_norm    res = x + y + bias ; out = LayerNorm(res)   (attention.py:239-243)
+//   vf_geglu             out = h[:, :k] * gelu(h[:, k:])              (attention.py:37-45)
+//   vf_add_bias          out = a + b + bias[c]                         (residual adds, conv bias)
+//
+// All are HBM-bound: every activation is read/written exactly once per kernel with 16-byte vectors,
+// statistics in fp32.  GroupNorm is two passes (statistics, apply): 2 reads + 1 write of x, against
+// 5 passes + 2 layout conversions for the eager GroupNorm(NCHW)/SiLU/add chain it replaces.
+#include "vf_common.cuh"
+
+namespace vf {
+
+template <typename T> struct V16;   // 16-byte vector of T as floats
+template <> struct V16<float> {
+  static constexpr int E = 4;
+  static __device__ __forceinline__ void ld(const float* p, float (&v)[4]) {
+    float4 t = *reinterpret_cast<const float4*>(p);
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  }
+  static __device__ __forceinline__ void st(float* p, const float (&v)[4]) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+};
+template <> struct V16<__nv_bfloat16> {
+  static constexpr int E = 8;
+  static __device__ __forceinline__ void ld(const __nv_bfloat16* p, float (&v)[8]) {
+    uint4 u = *reinterpret_cast<const uint4*>(p);
+    v[0] = bf16lo(u.x); v[1] = bf16hi(u.x); v[2] = bf16lo(u.y); v[3] = bf16hi(u.y);
+    v[4] = bf16lo(u.z); v[5] = bf16hi(u.z); v[6] = bf16lo(u.w); v[7] = bf16hi(u.w);
+  }
+  static __device__ __forceinline__ void st(__nv_bfloat16* p, const float (&v)[8]) {
+    *reinterpret_cast<uint4*>(p) = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+  }
+};
+
+// ================================================================================================
+// GroupNorm (NHWC)
+// ================================================================================================
+constexpr int kGnThreads = 256;
+constexpr int kGnMaxGroups = 32;
+
+struct GnParams {
+  const void* x; const void* add_nc; const void* gamma; const void* beta; void* y;
+  float* ws;            // [n][slabs][groups][2] partial (sum, sumsq)
+  int n, hw, c, groups, slabs, rows_per_slab;
+  float eps;
+  int silu;
+};
+
+// thread -> (row lane, chunk) mapping shared by both passes
+struct GnMap {
+  int chunks, tpr, rpb, my_row, my_chunk;
+  bool active;
+  __device__ GnMap(int c, int elems) {
+    chunks = c / elems;
+    tpr = chunks < kGnThreads ? chunks : kGnThreads;     // threads per row
+    rpb = kGnThreads / tpr;                               // rows per block iteration
+    my_row = threadIdx.x / tpr;
+    my_chunk = threadIdx.x - my_row * tpr;
+    active = my_row < rpb;
+  }
+};
+
+template <typename T, int CPT>    // CPT: chunks per thread along the channel axis (c/E <= 256*CPT)
+__global__ void __launch_bounds__(kGnThreads)
+gn_stats_kernel(const GnParams P) {
+  constexpr int E = V16<T>::E;
+  __shared__ float s_sum[kGnMaxGroups], s_sq[kGnMaxGroups];
+  const int n = blockIdx.y, slab = blockIdx.x;
+  if (threadIdx.x < kGnMaxGroups) { s_sum[threadIdx.x] = 0.f; s_sq[threadIdx.x] = 0.f; }
+  __syncthreads();
+  const GnMap M(P.c, E);
+  const int cpg = P.c / P.groups;
+  const int r0 = slab * P.rows_per_slab;
+  const int r1 = min(P.hw, r0 + P.rows_per_slab);
+  const T* x = reinterpret_cast<const T*>(P.x) + (size_t)n * P.hw * P.c;
+  const T* add = P.add_nc ? reinterpret_cast<const T*>(P.add_nc) + (size_t)n * P.c : nullptr;
+  if (M.active) {
+    float sum[CPT][E], sq[CPT][E], av[CPT][E];
+#pragma unroll
+    for (int k = 0; k < CPT; ++k) {
+      const int ch = (M.my_chunk + k * kGnThreads) * E;
+#pragma unroll
+      for (int j = 0; j < E; ++j) { sum[k][j] = 0.f; sq[k][j] = 0.f; av[k][j] = 0.f; }
+      if (add && ch < P.c) V16<T>::ld(add + ch, av[k]);
+    }
+    for (int r = r0 + M.my_row; r < r1; r += M.rpb) {
+#pragma unroll
+      for (int k = 0; k < CPT; ++k) {
+        const int ch = (M.my_chunk + k * kGnThreads) * E;
+        if (ch < P.c) {
+          float v[E];
+          V16<T>::ld(x + (size_t)r * P.c + ch, v);
+#pragma unroll
+          for (int j = 0; j < E; ++j) { const float t = v[j] + av[k][j]; sum[k][j] += t; sq[k][j] = fmaf(t, t, sq[k][j]); }
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < CPT; ++k) {
+      const int ch = (M.my_chunk + k * kGnThreads) * E;
+      if (ch < P.c) {
+#pragma unroll
+        for (int j = 0; j < E; ++j) {
+          const int g = (ch + j) / cpg;
+          atomicAdd(&s_sum[g], sum[k][j]);
+          atomicAdd(&s_sq[g], sq[k][j]);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < P.groups) {
+    float* w = P.ws + (((size_t)n * P.slabs + slab) * P.groups + threadIdx.x) * 2;
+    w[0] = s_sum[threadIdx.x];
+    w[1] = s_sq[threadIdx.x];
+  }
+}
+
+template <typename T, int CPT>
+__global__ void __launch_bounds__(kGnThreads)
+gn_apply_kernel(const GnParams P) {
+  constexpr int E = V16<T>::E;
+  __shared__ float s_mean[kGnMaxGroups], s_rstd[kGnMaxGroups];
+  const int n = blockIdx.y, slab = blockIdx.x;
+  const int cpg = P.c / P.groups;
+  if (threadIdx.x < P.groups) {
+    double s = 0.0, q = 0.0;
+    for (int i = 0; i < P.slabs; ++i) {
+      const float* w = P.ws + (((size_t)n * P.slabs + i) * P.groups + threadIdx.x) * 2;
+      s += (double)w[0];
+      q += (double)w[1];
+    }
+    const double cnt = (double)P.hw * cpg;
+    const double mean = s / cnt;
+    double var = q / cnt - mean * mean;
+    if (var < 0.0) var = 0.0;
+    s_mean[threadIdx.x] = (float)mean;
+    s_rstd[threadIdx.x] = (float)(1.0 / sqrt(var + (double)P.eps));
+  }
+  __syncthreads();
+  const GnMap M(P.c, E);
+  if (!M.active) return;
+  const int r0 = slab * P.rows_per_slab;
+  const int r1 = min(P.hw, r0 + P.rows_per_slab);
+  const T* x = reinterpret_cast<const T*>(P.x) + (size_t)n * P.hw * P.c;
+  T* y = reinterpret_cast<T*>(P.y) + (size_t)n * P.hw * P.c;
+  const T* add = P.add_nc ? reinterpret_cast<const T*>(P.add_nc) + (size_t)n * P.c : nullptr;
+  const T* gamma = reinterpret_cast<const T*>(P.gamma);
+  const T* beta = reinterpret_cast<const T*>(P.beta);
+  float scale[CPT][E], shift[CPT][E];
+#pragma unroll
+  for (int k = 0; k < CPT; ++k) {
+    const int ch = (M.my_chunk + k * kGnThreads) * E;
+    if (ch < P.c) {
+      float g[E], b[E], a[E];
+      V16<T>::ld(gamma + ch, g);
+      V16<T>::ld(beta + ch, b);
+#pragma unroll
+      for (int j = 0; j < E; ++j) a[j] = 0.f;
+      if (add) V16<T>::ld(add + ch, a);
+#pragma unroll
+      for (int j = 0; j < E; ++j) {
+        const int grp = (ch + j) / cpg;
+        scale[k][j] = s_rstd[grp] * g[j];
+        shift[k][j] = fmaf(a[j] - s_mean[grp], scale[k][j], b[j]);   // (x + a - mean) * rstd * gamma + beta
+      }
+    }
+  }
+  for (int r = r0 + M.my_row; r < r1; r += M.rpb) {
+#pragma unroll
+    for (int k = 0; k < CPT; ++k) {
+      const int ch = (M.my_chunk + k * kGnThreads) * E;
+      if (ch < P.c) {
+        float v[E];
+        V16<T>::ld(x + (size_t)r * P.c + ch, v);
+#pragma unroll
+        for (int j = 0; j < E; ++j) {
+          float t = fmaf(v[j], scale[k][j], shift[k][j]);
+          if (P.silu) t = t / (1.0f + __expf(-t));
+          v[j] = t;
+        }
+        V16<T>::st(y + (size_t)r * P.c + ch, v);
+      }
+    }
+  }
+}
+
+static void gn_plan(int n, int hw, int* slabs, int* rows_per_slab) {
+  int want = (4 * num_sms() + n - 1) / n;
+  if (want < 1) want = 1;
+  if (want > 64) want = 64;
+  int rps = (hw + want - 1) / want;
+  if (rps < 8) rps = hw < 8 ? hw : 8;
+  *rows_per_slab = rps;
+  *slabs = (hw + rps - 1) / rps;
+}
+
+// ================================================================================================
+// residual add + bias + LayerNorm (one warp per row)
+// ================================================================================================
+constexpr int kLnWarps = 8;
+
+struct LnParams {
+  const void* x; const void* y; const void* bias; const void* gamma; const void* beta;
+  void* res; void* out;
+  long long rows, rows_per_bias;
+  int c;
+  float eps;
+};
+
+template <typename T, int MAXC>   // MAXC: 16-byte chunks per lane
+__global__ void __launch_bounds__(kLnWarps * 32)
+add_layer_norm_kernel(const LnParams P) {
+  constexpr int E = V16<T>::E;
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * kLnWarps + (threadIdx.x >> 5);
+  if (row >= P.rows) return;
+  const int chunks = P.c / E;
+  const T* x = reinterpret_cast<const T*>(P.x) + row * P.c;
+  const T* y = P.y ? reinterpret_cast<const T*>(P.y) + row * P.c : nullptr;
+  const T* bias = nullptr;
+  if (P.bias) bias = reinterpret_cast<const T*>(P.bias) + (P.rows_per_bias > 0 ? (row / P.rows_per_bias) * P.c : 0);
+  float v[MAXC][E];
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < MAXC; ++k) {
+    const int ch = lane + 32 * k;
+    if (ch < chunks) {
+      V16<T>::ld(x + ch * E, v[k]);
+      if (y) {
+        float t[E];
+        V16<T>::ld(y + ch * E, t);
+#pragma unroll
+        for (int j = 0; j < E; ++j) v[k][j] += t[j];
+      }
+      if (bias) {
+        float t[E];
+        V16<T>::ld(bias + ch * E, t);
+#pragma unroll
+        for (int j = 0; j < E; ++j) v[k][j] += t[j];
+      }
+      if (P.res) {
+        // the residual stream is stored in T; normalise what was stored so both consumers agree
+        V16<T>::st(reinterpret_cast<T*>(P.res) + row * P.c + ch * E, v[k]);
+        if (sizeof(T) == 2) {
+#pragma unroll
+          for (int j = 0; j < E; ++j) v[k][j] = __bfloat162float(__float2bfloat16_rn(v[k][j]));
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < E; ++j) s += v[k][j];
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s / (float)P.c;
+  float q = 0.f;
+#pragma unroll
+  for (int k = 0; k < MAXC; ++k) {
+    if (lane + 32 * k < chunks) {
+#pragma unroll
+      for (int j = 0; j < E; ++j) { const float t = v[k][j] - mean; q = fmaf(t, t, q); }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  const float rstd = rsqrtf(q / (float)P.c + P.eps);
+  const T* gamma = reinterpret_cast<const T*>(P.gamma);
+  const T* beta = reinterpret_cast<const T*>(P.beta);
+  T* out = reinterpret_cast<T*>(P.out) + row * P.c;
+#pragma unroll
+  for (int k = 0; k < MAXC; ++k) {
+    const int ch = lane + 32 * k;
+    if (ch < chunks) {
+      float g[E], b[E];
+      V16<T>::ld(gamma + ch * E, g);
+      V16<T>::ld(beta + ch * E, b);
+#pragma unroll
+      for (int j = 0; j < E; ++j) v[k][j] = fmaf((v[k][j] - mean) * rstd, g[j], b[j]);
+      V16<T>::st(out + ch * E, v[k]);
+    }
+  }
+}
+
+// ================================================================================================
+// GEGLU and residual add
+// ================================================================================================
+template <typename T>
+__global__ void __launch_bounds__(256)
+geglu_kernel(const T* __restrict__ h, T* __restrict__ out, long long rows, int k, long long ld_h) {
+  constexpr int E = V16<T>::E;
+  const int chunks = k / E;
+  const long long total = rows * chunks;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / chunks;
+    const int ch = (int)(i - r * chunks) * E;
+    float a[E], g[E];
+    V16<T>::ld(h + r * ld_h + ch, a);
+    V16<T>::ld(h + r * ld_h + k + ch, g);
+#pragma unroll
+    for (int j = 0; j < E; ++j) a[j] *= 0.5f * g[j] * (1.0f + erff(g[j] * 0.70710678118654752f));   // exact (erf) GELU
+    V16<T>::st(out + r * (long long)k + ch, a);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+add_bias_kernel(const T* __restrict__ a, const T* __restrict__ b, const T* __restrict__ bias, T* __restrict__ out,
+                long long rows, int c, long long rows_per_bias) {
+  constexpr int E = V16<T>::E;
+  const int chunks = c / E;
+  const long long total = rows * chunks;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / chunks;
+    const int ch = (int)(i - r * chunks) * E;
+    float va[E];
+    V16<T>::ld(a + r * c + ch, va);
+    if (b) {
+      float vb[E];
+      V16<T>::ld(b + r * c + ch, vb);
+#pragma unroll
+      for (int j = 0; j < E; ++j) va[j] += vb[j];
+    }
+    if (bias) {
+      float vc[E];
+      V16<T>::ld(bias + (rows_per_bias > 0 ? (r / rows_per_bias) * c : 0) + ch, vc);
+#pragma unroll
+      for (int j = 0; j < E; ++j) va[j] += vc[j];
+    }
+    V16<T>::st(out + r * c + ch, va);
+  }
+}
+
+static int ew_grid(long long total) {
+  long long blocks = (total + 255) / 256;
+  const long long cap = (long long)num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+static bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+}  // namespace vf
+
+extern "C" long long vf_group_norm_workspace_floats(int n, int hw, int groups) {
+  int slabs, rps;
+  if (n <= 0 || hw <= 0 || groups <= 0) return 0;
+  vf::gn_plan(n, hw, &slabs, &rps);
+  return (long long)n * slabs * groups * 2;
+}
+
+extern "C" int vf_group_norm_nhwc(const void* x, const void* add_nc, const void* gamma, const void* beta, void* y,
+                                  float* workspace, int n, int hw, int c, int groups, float eps, int silu,
+                                  int dtype, void* stream) {
+  using namespace vf;
+  if (int rc = check_device()) return rc;
+  if (!x || !gamma || !beta || !y || !workspace) return fail("vf_group_norm_nhwc: null pointer");
+  if (dtype != VF_F32 && dtype != VF_BF16) return fail("vf_group_norm_nhwc: bad dtype %d", dtype);
+  const int e = dtype == VF_F32 ? 4 : 8;
+  if (n <= 0 || hw <= 0 || c <= 0 || groups <= 0 || groups > kGnMaxGroups || c % groups || c % e)
+    return fail("vf_group_norm_nhwc: bad shape n=%d hw=%d c=%d groups=%d", n, hw, c, groups);
+  if (c / e > 3 * kGnThreads) return fail("vf_group_norm_nhwc: c=%d too wide", c);
+  if (n > 65535) return fail("vf_group_norm_nhwc: n=%d exceeds 65535", n);
+  if (!al16(x) || !al16(y) || !al16(gamma) || !al16(beta) || (add_nc && !al16(add_nc)))
+    return fail("vf_group_norm_nhwc: pointers must be 16-byte aligned");
+  GnParams P;
+  P.x = x; P.add_nc = add_nc; P.gamma = gamma; P.beta = beta; P.y = y; P.ws = workspace;
+  P.n = n; P.hw = hw; P.c = c; P.groups = groups; P.eps = eps; P.silu = silu;
+  gn_plan(n, hw, &P.slabs, &P.rows_per_slab);
+  dim3 grid(P.slabs, n);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int cpt = (c / e + kGnThreads - 1) / kGnThreads;
+#define VF_GN_LAUNCH(T, K)                                        \
+  do {                                                            \
+    gn_stats_kernel<T, K><<<grid, kGnThreads, 0, st>>>(P);        \
+    gn_apply_kernel<T, K><<<grid, kGnThreads, 0, st>>>(P);        \
+  } while (0)
+  if (dtype == VF_F32) {
+    if (cpt == 1) VF_GN_LAUNCH(float, 1); else if (cpt == 2) VF_GN_LAUNCH(float, 2); else VF_GN_LAUNCH(float, 3);
+  } else {
+    if (cpt == 1) VF_GN_LAUNCH(__nv_bfloat16, 1); else if (cpt == 2) VF_GN_LAUNCH(__nv_bfloat16, 2); else VF_GN_LAUNCH(__nv_bfloat16, 3);
+  }
+#undef VF_GN_LAUNCH
+  return check_cuda(cudaGetLastError(), "group_norm kernels launch");
+}
+
+extern "C" int vf_add_layer_norm(const void* x, const void* y, const void* bias, long long rows_per_bias,
+                                 const void* gamma, const void* beta, void* res, void* out,
+                                 long long rows, int c, float eps, int dtype, void* stream) {
+  using namespace vf;
+  if (int rc = check_device()) return rc;
+  if (!x || !gamma || !beta || !out) return fail("vf_add_layer_norm: null pointer");
+  if (dtype != VF_F32 && dtype != VF_BF16) return fail("vf_add_layer_norm: bad dtype %d", dtype);
+  const int e = dtype == VF_F32 ? 4 : 8;
+  if (rows <= 0 || c <= 0 || c % e) return fail("vf_add_layer_norm: bad shape rows=%lld c=%d", rows, c);
+  const int per_lane = (c / e + 31) / 32;
+  if (per_lane > 10) return fail("vf_add_layer_norm: c=%d too wide", c);
+  if ((y || bias) && !res) return fail("vf_add_layer_norm: res is required when y or bias is given");
+  if (!al16(x) || !al16(out) || !al16(gamma) || !al16(beta) || (y && !al16(y)) || (bias && !al16(bias)) || (res && !al16(res)))
+    return fail("vf_add_layer_norm: pointers must be 16-byte aligned");
+  LnParams P;
+  P.x = x; P.y = y; P.bias = bias; P.gamma = gamma; P.beta = beta; P.res = res; P.out = out;
+  P.rows = rows; P.rows_per_bias = rows_per_bias; P.c = c; P.eps = eps;
+  const long long blocks = (rows + kLnWarps - 1) / kLnWarps;
+  if (blocks > 2147483647LL) return fail("vf_add_layer_norm: too many rows");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int thr = kLnWarps * 32;
+#define VF_LN_LAUNCH(T)                                                                   \
+  do {                                                                                    \
+    if (per_lane <= 2) add_layer_norm_kernel<T, 2><<<(int)blocks, thr, 0, st>>>(P);        \
+    else if (per_lane <= 5) add_layer_norm_kernel<T, 5><<<(int)blocks, thr, 0, st>>>(P);   \
+    else add_layer_norm_kernel<T, 10><<<(int)blocks, thr, 0, st>>>(P);                     \
+  } while (0)
+  if (dtype == VF_F32) VF_LN_LAUNCH(float); else VF_LN_LAUNCH(__nv_bfloat16);
+#undef VF_LN_LAUNCH
+  return check_cuda(cudaGetLastError(), "add_layer_norm_kernel launch");
+}
+
+extern "C" int vf_geglu(const void* h, void* out, long long rows, int k, long long ld_h, int dtype, void* stream) {
+  using namespace vf;
+  if (int rc = check_device()) return rc;
+  if (!h || !out) return fail("vf_geglu: null pointer");
+  if (dtype != VF_F32 && dtype != VF_BF16) return fail("vf_geglu: bad dtype %d", dtype);
+  const int e = dtype == VF_F32 ? 4 : 8;
+  if (rows <= 0 || k <= 0 || k % e || ld_h < 2LL * k || ld_h % e) return fail("vf_geglu: bad shape rows=%lld k=%d ld=%lld", rows, k, ld_h);
+  if (!al16(h) || !al16(out)) return fail("vf_geglu: pointers must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = ew_grid(rows * (k / e));
+  if (dtype == VF_F32) geglu_kernel<float><<<grid, 256, 0, st>>>((const float*)h, (float*)out, rows, k, ld_h);
+  else geglu_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)h, (__nv_bfloat16*)out, rows, k, ld_h);
+  return check_cuda(cudaGetLastError(), "geglu_kernel launch");
+}
+
+extern "C" int vf_add_bias(const void* a, const void* b, const void* bias, long long rows_per_bias, void* out,
+                           long long rows, int c, int dtype, void* stream) {
+  using namespace vf;
+  if (int rc = check_device()) return rc;
+  if (!a || !out) return fail("vf_add_bias: null pointer");
+  if (dtype != VF_F32 && dtype != VF_BF16) return fail("vf_add_bias: bad dtype %d", dtype);
+  const int e = dtype == VF_F32 ? 4 : 8;
+  if (rows <= 0 || c <= 0 || c % e) return fail("vf_add_bias: bad shape rows=%lld c=%d", rows, c);
+  if (!al16(a) || !al16(out) || (b && !al16(b)) || (bias && !al16(bias))) return fail("vf_add_bias: pointers must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = ew_grid(rows * (c / e));
+  if (dtype == VF_F32)
+    add_bias_kernel<float><<<grid, 256, 0, st>>>((const float*)a, (const float*)b, (const float*)bias, (float*)out, rows, c, rows_per_bias);
+  else
+    add_bias_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)a, (const __nv_bfloat16*)b, (const __nv_bfloat16*)bias,
+                                                          (__nv_bfloat16*)out, rows, c, rows_per_bias);
+  return check_cuda(cudaGetLastError(), "add_bias_kernel launch");
+}

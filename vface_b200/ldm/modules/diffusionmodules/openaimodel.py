@@ -20,6 +20,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from .... import ops
 from ..attention import SpatialTransformer
 from .util import normalization, timestep_embedding, zero_module
 
@@ -104,11 +105,29 @@ class ResBlock(TimestepBlock):
         return self._forward(x, emb)
 
     def _forward(self, x, emb):
-        h = self.in_layers(x)
-        emb_out = self.emb_layers(emb).type(h.dtype)
-        h = h + emb_out[:, :, None, None]
-        h = self.out_layers(h)
-        return self.skip_connection(x) + h
+        """GN-SiLU-conv, + emb, GN-SiLU-conv, + skip (reference :255-275) on channels-last activations:
+        the two GroupNorm+SiLU are one fused kernel each, the `+ emb_out` and the first conv bias ride
+        inside the second GroupNorm, and the second conv bias rides inside the residual add."""
+        n, c, hh, ww = x.shape
+        xt = x.permute(0, 2, 3, 1).contiguous()                  # NHWC; a view for channels_last input
+        gn1, conv1 = self.in_layers[0], self.in_layers[2]
+        gn2, conv2 = self.out_layers[0], self.out_layers[3]
+        g1 = ops.group_norm_nhwc(xt, gn1.weight, gn1.bias, gn1.eps, gn1.num_groups, silu=True)
+        h1 = F.conv2d(g1.permute(0, 3, 1, 2), conv1.weight, None, padding=1)
+        add = self.emb_layers(emb).type(h1.dtype) + conv1.bias
+        g2 = ops.group_norm_nhwc(h1.permute(0, 2, 3, 1).contiguous(), gn2.weight, gn2.bias, gn2.eps, gn2.num_groups,
+                                 silu=True, add_nc=add)
+        h2 = F.conv2d(g2.permute(0, 3, 1, 2), conv2.weight, None, padding=1).permute(0, 2, 3, 1).contiguous()
+        bias = conv2.bias
+        if isinstance(self.skip_connection, nn.Identity):
+            skip = xt
+        elif self.skip_connection.kernel_size == (1, 1):
+            skip = F.linear(xt, self.skip_connection.weight.reshape(self.out_channels, c))
+            bias = bias + self.skip_connection.bias
+        else:
+            skip = self.skip_connection(x).permute(0, 2, 3, 1).contiguous()
+        out = ops.add_bias(skip, h2, bias)
+        return out.permute(0, 3, 1, 2)
 
 
 class UNetModel(nn.Module):
@@ -216,6 +235,17 @@ class UNetModel(nn.Module):
         if y is not None:
             raise NotImplementedError("class-conditional UNet is not used by the VFace configuration")
         dt = self.dtype
+        if dt == torch.float32:
+            # reference-precision path: keep cuDNN convolutions in true fp32 (no TF32)
+            with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+                return self._forward(x, timesteps, context, return_features)
+        return self._forward(x, timesteps, context, return_features)
+
+    def _forward(self, x, timesteps, context, return_features):
+        dt = self.dtype
+        if not getattr(self, "_weights_channels_last", False):
+            self.to(memory_format=torch.channels_last)       # conv weights NHWC once; keys/values unchanged
+            self._weights_channels_last = True
         emb = self.time_embed(timestep_embedding(timesteps, self.model_channels).to(dt))
         context = context.to(dt)
         h = x.to(dt).contiguous(memory_format=torch.channels_last)
@@ -230,5 +260,7 @@ class UNetModel(nn.Module):
             h = module(h, emb, context)
             if return_features:
                 features.append(h)
-        out = self.out(h).to(x.dtype).contiguous()
+        gn = self.out[0]
+        ht = ops.group_norm_nhwc(h.permute(0, 2, 3, 1).contiguous(), gn.weight, gn.bias, gn.eps, gn.num_groups, silu=True)
+        out = self.out[2](ht.permute(0, 3, 1, 2)).to(x.dtype).contiguous()
         return (out, features) if return_features else out

@@ -22,6 +22,25 @@ def _count(n=1):
     launch_count += n
 
 
+_attn_prof = None   # (min_tokens, [(start_event, end_event), ...]) while profiling
+
+
+def profile_attention(min_tokens):
+    """Live timing of the attention kernel for the roofline in bench.py: profile_attention(n) starts
+    recording CUDA events (on the launching stream) around every vf_attn_fwd launch with n_q >= n;
+    profile_attention(None) stops and returns the per-launch durations in ms."""
+    global _attn_prof
+    if min_tokens is not None:
+        _attn_prof = (int(min_tokens), [])
+        return None
+    if _attn_prof is None:
+        return []
+    torch.cuda.synchronize()
+    out = [a.elapsed_time(b) for a, b in _attn_prof[1]]
+    _attn_prof = None
+    return out
+
+
 def _code(t: torch.Tensor) -> int:
     if t.dtype == torch.float32:
         return VF_F32
@@ -80,9 +99,16 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, sca
             raise ValueError("attention: bad k2/v2")
         p_k2, p_v2 = k2.data_ptr(), v2.data_ptr()
     lib = _lib.load()
+    prof = _attn_prof is not None and n_q >= _attn_prof[0]
+    if prof:
+        ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        ev[0].record()
     rc = lib.vf_attn_fwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), b, heads, n_q, n_kv, d,
                          ld_q, ld_k, ld_v, ld_o, float(scale), p_k2, p_v2, n_kv2, ld_k2, ld_v2,
                          _code(q), _stream(q))
+    if prof:
+        ev[1].record()
+        _attn_prof[1].append(ev)
     _lib.check(rc, "vf_attn_fwd")
     _count()
     return out
@@ -220,3 +246,99 @@ def ddim_invert_step(x: torch.Tensor, e_cond: torch.Tensor, a_cur: float, a_next
     _lib.check(rc, "vf_ddim_invert_step")
     _count()
     return x_next
+
+
+# ---- fused glue kernels of the UNet (vf_norm.cu) ---------------------------------------------------------
+def _rows_c(t: torch.Tensor, name: str):
+    if not t.is_contiguous():
+        raise ValueError(f"{name}: expected a contiguous (..., c) tensor, got strides {t.stride()}")
+    c = t.shape[-1]
+    return t.numel() // c, c
+
+
+def group_norm_nhwc(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, eps: float, groups: int = 32,
+                    silu: bool = False, add_nc: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """GroupNorm (+SiLU) of channels-last activations x: (n, ..., c); add_nc: optional (n, c) vector
+    added to every position before the statistics (ResBlock `h + emb_out`)."""
+    _need_cuda(x, weight, bias, add_nc)
+    if not x.is_contiguous() or x.dim() < 3:
+        raise ValueError("group_norm_nhwc: x must be a contiguous (n, ..., c) tensor")
+    n, c = x.shape[0], x.shape[-1]
+    hw = x.numel() // (n * c)
+    if weight.dtype != x.dtype or bias.dtype != x.dtype or (add_nc is not None and (add_nc.dtype != x.dtype or tuple(add_nc.shape) != (n, c))):
+        raise ValueError("group_norm_nhwc: parameter dtype/shape mismatch")
+    lib = _lib.load()
+    ws = torch.empty(lib.vf_group_norm_workspace_floats(n, hw, groups), dtype=torch.float32, device=x.device)
+    y = torch.empty_like(x)
+    rc = lib.vf_group_norm_nhwc(x.data_ptr(), add_nc.contiguous().data_ptr() if add_nc is not None else None,
+                                weight.data_ptr(), bias.data_ptr(), y.data_ptr(), ws.data_ptr(), n, hw, c, groups,
+                                float(eps), int(silu), _code(x), _stream(x))
+    _lib.check(rc, "vf_group_norm_nhwc")
+    _count(2)
+    return y
+
+
+def add_layer_norm(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, eps: float = 1e-5,
+                   y: Optional[torch.Tensor] = None, row_bias: Optional[torch.Tensor] = None):
+    """res = x + y + row_bias ; out = LayerNorm(res).  row_bias: (c,) or (n, c) for x of shape (n, m, c).
+    Returns out when neither y nor row_bias is given, else (res, out)."""
+    _need_cuda(x, weight, bias, y, row_bias)
+    rows, c = _rows_c(x, "x")
+    if y is not None and (y.shape != x.shape or y.dtype != x.dtype or not y.is_contiguous()):
+        raise ValueError("add_layer_norm: y must match x and be contiguous")
+    rpb = 0
+    if row_bias is not None:
+        row_bias = row_bias.contiguous()
+        if row_bias.dtype != x.dtype or row_bias.shape[-1] != c:
+            raise ValueError("add_layer_norm: bad row_bias")
+        nb = row_bias.numel() // c
+        if nb > 1:
+            if rows % nb:
+                raise ValueError("add_layer_norm: rows not divisible by bias rows")
+            rpb = rows // nb
+    fused = y is not None or row_bias is not None
+    res = torch.empty_like(x) if fused else None
+    out = torch.empty_like(x)
+    lib = _lib.load()
+    rc = lib.vf_add_layer_norm(x.data_ptr(), y.data_ptr() if y is not None else None,
+                               row_bias.data_ptr() if row_bias is not None else None, rpb, weight.data_ptr(), bias.data_ptr(),
+                               res.data_ptr() if fused else None, out.data_ptr(), rows, c, float(eps), _code(x), _stream(x))
+    _lib.check(rc, "vf_add_layer_norm")
+    _count()
+    return (res, out) if fused else out
+
+
+def geglu(h: torch.Tensor) -> torch.Tensor:
+    """h (..., 2k) -> h[..., :k] * gelu(h[..., k:])  (exact erf GELU, attention.py:43-45)."""
+    _need_cuda(h)
+    rows, two_k = _rows_c(h, "h")
+    k = two_k // 2
+    out = torch.empty(h.shape[:-1] + (k,), dtype=h.dtype, device=h.device)
+    lib = _lib.load()
+    rc = lib.vf_geglu(h.data_ptr(), out.data_ptr(), rows, k, two_k, _code(h), _stream(h))
+    _lib.check(rc, "vf_geglu")
+    _count()
+    return out
+
+
+def add_bias(a: torch.Tensor, b: Optional[torch.Tensor] = None, row_bias: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """a + b + row_bias over contiguous (..., c) tensors; row_bias (c,) or (n, c)."""
+    _need_cuda(a, b, row_bias)
+    rows, c = _rows_c(a, "a")
+    if b is not None and (b.shape != a.shape or b.dtype != a.dtype or not b.is_contiguous()):
+        raise ValueError("add_bias: b must match a and be contiguous")
+    rpb = 0
+    if row_bias is not None:
+        row_bias = row_bias.contiguous()
+        if row_bias.dtype != a.dtype or row_bias.shape[-1] != c:
+            raise ValueError("add_bias: bad row_bias")
+        nb = row_bias.numel() // c
+        if nb > 1:
+            rpb = rows // nb
+    out = torch.empty_like(a)
+    lib = _lib.load()
+    rc = lib.vf_add_bias(a.data_ptr(), b.data_ptr() if b is not None else None,
+                         row_bias.data_ptr() if row_bias is not None else None, rpb, out.data_ptr(), rows, c, _code(a), _stream(a))
+    _lib.check(rc, "vf_add_bias")
+    _count()
+    return out
