@@ -5,33 +5,39 @@
 //   optional second K/V segment concatenated along the key axis (injected target-frame K/V).
 //
 // Design (sm_100a):
-//   * one CTA = one 128-row query tile of one (batch, head); 6 warps:
-//       warp 0      TMA producer  (cp.async.bulk.tensor 4-D boxes, 128B swizzle, zero fill of the
-//                                  head-dim padding d -> 64k and of ragged row tails)
-//       warp 1      tcgen05.mma issuer + TMEM allocator (one elected lane issues)
-//       warps 2..5  softmax / correction / epilogue, one thread per query row (TMEM lane)
+//   * one CTA = one 128-row query tile of one (batch, head); 8 warps in two warpgroups:
+//       warpgroup 0  warp 0 = TMA producer (cp.async.bulk.tensor 4-D boxes, 128B swizzle, zero fill of
+//                             the head-dim padding d -> 64k and of ragged row tails),
+//                    warp 1 = tcgen05.mma issuer + TMEM allocator (one elected lane issues),
+//                    warps 2,3 idle; the group gives its registers away (setmaxnreg.dec)
+//       warpgroup 1  softmax / correction / epilogue, one thread per query row (TMEM lane),
+//                    with the registers of warpgroup 0 added (setmaxnreg.inc)
 //   * S = Q K^T      : tcgen05.mma  SS, M=128, N=BN, K=16 x ceil(d/16), fp32 accumulator in TMEM
-//   * P (bf16)       : written back to TMEM by the softmax threads (tcgen05.st), never to smem/HBM
+//   * P (bf16)       : written back over the first BN/2 columns of S by the softmax threads
+//                      (tcgen05.st) once S is in registers -- never to smem/HBM
 //   * O += P V       : tcgen05.mma  TS (A = P from TMEM), B = V tile in MN-major 128B-swizzled smem
+//   * the tensor pipe executes in issue order, so PV_j followed by QK_{j+1} may reuse the S/P columns
 //   * online softmax in the exp2 domain with lazy rescaling of O (only when the running max moves
-//     by more than 2^8), so the correction pass is rare
-//   * K and V rings are separate 2-stage mbarrier pipelines; S_{j+1} is issued while the softmax of
-//     tile j runs, and two CTAs are resident per SM so their softmax and MMA phases interleave.
+//     by more than 2^8), so the correction pass is rare; FMNMX3 / FFMA2 / FADD2 keep the per-element
+//     instruction count at ~3 so that the kernel is bound by MUFU.EX2, not by issue slots
+//   * small CTAs (BN = 64: 48 KB smem, 128 TMEM columns at d <= 64) so that FOUR CTAs are resident per
+//     SM: 4 softmax warps per SM sub-partition interleave their MUFU, TMEM-load and barrier phases.
 //   * the head dimension is NOT padded in HBM: the TMA box is 64 elements wide over a tensor-map
 //     dimension of extent d, out-of-bounds columns are zero-filled in shared memory.
 //
-// TMEM columns: [0,BN) S fp32 | [BN, BN+BN/2) P bf16x2 | [BN+BN/2, +d_pad) O fp32.
+// TMEM columns: [0,BN) S fp32, aliased by P bf16x2 in [0,BN/2) | [BN, BN+d_pad) O fp32.
 #include "vf_attn.cuh"
 #include "vf_sm100.cuh"
 
 #include <cuda.h>
 #include <cmath>
+#include <cstdlib>
 
 namespace vf {
 
 using namespace sm100;
 
-constexpr int kTcThreads = 192;
+constexpr int kTcThreads = 256;
 constexpr int kBM = 128;            // query rows per CTA
 constexpr float kRescaleThreshold = 8.0f;   // log2 units
 
@@ -46,12 +52,18 @@ struct __align__(8) TcBarriers {
   uint64_t q_full;
   uint64_t k_full[2], k_empty[2];
   uint64_t v_full[2], v_empty[2];
-  uint64_t s_full, s_empty, p_full, o_done;
+  uint64_t s_full, p_full, o_done;
   uint32_t tmem_base;
 };
 
-template <int BN, int kTmemCols>
-__global__ void __launch_bounds__(kTcThreads, 2)
+template <int kRegs> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" :: "n"(kRegs)); }
+template <int kRegs> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" :: "n"(kRegs)); }
+
+// kMinBlocks CTAs per SM; with 4 the launch-time register budget is 64 per thread and the softmax
+// warpgroup is raised to 104 with the 40 that warpgroup 0 gives up.
+// kEmu of every 4 score pairs take their exp2 on the FMA pipe (polynomial) instead of MUFU.
+template <int BN, int kTmemCols, int kMinBlocks, int kEmu>
+__global__ void __launch_bounds__(kTcThreads, kMinBlocks)
 attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                const __grid_constant__ CUtensorMap map_v, const __grid_constant__ CUtensorMap map_k2,
                const __grid_constant__ CUtensorMap map_v2, const AttnTcParams P) {
@@ -89,7 +101,6 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
       mbar_init(&bars.v_empty[s], 1);
     }
     mbar_init(&bars.s_full, 1);
-    mbar_init(&bars.s_empty, 4);
     mbar_init(&bars.p_full, 4);
     mbar_init(&bars.o_done, 1);
     fence_barrier_init();
@@ -99,84 +110,85 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = bars.tmem_base;
-  const uint32_t tm_s = tmem;
-  const uint32_t tm_p = tmem + BN;
-  const uint32_t tm_o = tmem + BN + BN / 2;
+  const uint32_t tm_s = tmem;          // S (fp32, BN columns); P (bf16x2) overwrites its first BN/2 columns
+  const uint32_t tm_p = tmem;
+  const uint32_t tm_o = tmem + BN;
 
-  if (warp == 0) {
-    // =========================== TMA producer ====================================================
-    if (lane == 0) {
-      tma_prefetch_desc(&map_q);
-      tma_prefetch_desc(&map_k);
-      tma_prefetch_desc(&map_v);
-      mbar_arrive_expect_tx(&bars.q_full, q_bytes);
-      for (int kb = 0; kb < P.kb; ++kb)
-        tma_load_4d(sQ + kb * q_block_bytes, &map_q, &bars.q_full, kb * 64, h, q_tile * kBM, b);
-      for (int j = 0; j < n_tiles; ++j) {
-        const int st = j & 1;
-        const uint32_t use = (uint32_t)(j >> 1);
-        const bool seg2 = j >= t1;
-        const int row0 = (seg2 ? j - t1 : j) * BN;
-        const CUtensorMap* mk = seg2 ? &map_k2 : &map_k;
-        const CUtensorMap* mv = seg2 ? &map_v2 : &map_v;
-        mbar_wait(&bars.k_empty[st], (use & 1) ^ 1);
-        mbar_arrive_expect_tx(&bars.k_full[st], kv_bytes);
+  if (warp < 4) {
+    if (kMinBlocks >= 4) reg_dec<24>();
+    if (warp == 0) {
+      // =========================== TMA producer ==================================================
+      if (lane == 0) {
+        tma_prefetch_desc(&map_q);
+        tma_prefetch_desc(&map_k);
+        tma_prefetch_desc(&map_v);
+        mbar_arrive_expect_tx(&bars.q_full, q_bytes);
         for (int kb = 0; kb < P.kb; ++kb)
-          tma_load_4d(sK + st * kv_bytes + kb * kv_block_bytes, mk, &bars.k_full[st], kb * 64, h, row0, b);
-        mbar_wait(&bars.v_empty[st], (use & 1) ^ 1);
-        mbar_arrive_expect_tx(&bars.v_full[st], kv_bytes);
-        for (int kb = 0; kb < P.kb; ++kb)
-          tma_load_4d(sV + st * kv_bytes + kb * kv_block_bytes, mv, &bars.v_full[st], kb * 64, h, row0, b);
+          tma_load_4d(sQ + kb * q_block_bytes, &map_q, &bars.q_full, kb * 64, h, q_tile * kBM, b);
+        for (int j = 0; j < n_tiles; ++j) {
+          const int st = j & 1;
+          const uint32_t use = (uint32_t)(j >> 1);
+          const bool seg2 = j >= t1;
+          const int row0 = (seg2 ? j - t1 : j) * BN;
+          const CUtensorMap* mk = seg2 ? &map_k2 : &map_k;
+          const CUtensorMap* mv = seg2 ? &map_v2 : &map_v;
+          mbar_wait(&bars.k_empty[st], (use & 1) ^ 1);
+          mbar_arrive_expect_tx(&bars.k_full[st], kv_bytes);
+          for (int kb = 0; kb < P.kb; ++kb)
+            tma_load_4d(sK + st * kv_bytes + kb * kv_block_bytes, mk, &bars.k_full[st], kb * 64, h, row0, b);
+          mbar_wait(&bars.v_empty[st], (use & 1) ^ 1);
+          mbar_arrive_expect_tx(&bars.v_full[st], kv_bytes);
+          for (int kb = 0; kb < P.kb; ++kb)
+            tma_load_4d(sV + st * kv_bytes + kb * kv_block_bytes, mv, &bars.v_full[st], kb * 64, h, row0, b);
+        }
       }
-    }
-  } else if (warp == 1) {
-    // =========================== MMA issuer ======================================================
-    if (lane == 0) {
-      const uint32_t idesc_qk = make_idesc_bf16(kBM, BN, false);
-      const uint32_t idesc_pv = make_idesc_bf16(kBM, P.d_pad, true);
-      const int k_steps = P.d_pad / 16;
-      const uint32_t q_addr = smem_u32(sQ);
-      const uint32_t k_addr = smem_u32(sK);
-      const uint32_t v_addr = smem_u32(sV);
+    } else if (warp == 1) {
+      // =========================== MMA issuer ====================================================
+      if (lane == 0) {
+        const uint32_t idesc_qk = make_idesc_bf16(kBM, BN, false);
+        const uint32_t idesc_pv = make_idesc_bf16(kBM, P.d_pad, true);
+        const int k_steps = P.d_pad / 16;
+        const uint32_t q_addr = smem_u32(sQ);
+        const uint32_t k_addr = smem_u32(sK);
+        const uint32_t v_addr = smem_u32(sV);
 
-      auto issue_qk = [&](int j) {
-        const int st = j & 1;
-        mbar_wait(&bars.k_full[st], (uint32_t)(j >> 1) & 1);
-        tc_fence_after();
-        for (int s = 0; s < k_steps; ++s) {
-          const uint32_t off_blk = (uint32_t)(s >> 2), off_in = (uint32_t)(s & 3) * 32u;
-          const uint64_t da = make_smem_desc_sw128(q_addr + off_blk * q_block_bytes + off_in, 16, 1024);
-          const uint64_t db = make_smem_desc_sw128(k_addr + st * kv_bytes + off_blk * kv_block_bytes + off_in, 16, 1024);
-          mma_ss(tm_s, da, db, idesc_qk, s > 0);
-        }
-        tc_commit(&bars.k_empty[st]);
-        tc_commit(&bars.s_full);
-      };
+        auto issue_qk = [&](int j) {
+          const int st = j & 1;
+          mbar_wait(&bars.k_full[st], (uint32_t)(j >> 1) & 1);
+          tc_fence_after();
+          for (int s = 0; s < k_steps; ++s) {
+            const uint32_t off_blk = (uint32_t)(s >> 2), off_in = (uint32_t)(s & 3) * 32u;
+            const uint64_t da = make_smem_desc_sw128(q_addr + off_blk * q_block_bytes + off_in, 16, 1024);
+            const uint64_t db = make_smem_desc_sw128(k_addr + st * kv_bytes + off_blk * kv_block_bytes + off_in, 16, 1024);
+            mma_ss(tm_s, da, db, idesc_qk, s > 0);
+          }
+          tc_commit(&bars.k_empty[st]);
+          tc_commit(&bars.s_full);
+        };
 
-      mbar_wait(&bars.q_full, 0);
-      issue_qk(0);
-      for (int j = 0; j < n_tiles; ++j) {
-        if (j + 1 < n_tiles) {
-          mbar_wait(&bars.s_empty, (uint32_t)j & 1);     // softmax has S_j in registers
-          issue_qk(j + 1);
-        }
-        const int st = j & 1;
-        mbar_wait(&bars.v_full[st], (uint32_t)(j >> 1) & 1);
-        mbar_wait(&bars.p_full, (uint32_t)j & 1);        // P_j in TMEM, O rescaled if needed
-        tc_fence_after();
+        mbar_wait(&bars.q_full, 0);
+        issue_qk(0);
+        for (int j = 0; j < n_tiles; ++j) {
+          const int st = j & 1;
+          mbar_wait(&bars.v_full[st], (uint32_t)(j >> 1) & 1);
+          mbar_wait(&bars.p_full, (uint32_t)j & 1);        // P_j in TMEM (over S_j), O rescaled if needed
+          tc_fence_after();
 #pragma unroll 1
-        for (int s = 0; s < BN / 16; ++s) {
-          // B = V tile, MN-major: 64 head-dim elements contiguous (128 B) per key row, 8-row groups
-          // 1024 B apart (SBO), further 64-wide head-dim blocks kv_block_bytes apart (LBO).
-          const uint64_t db = make_smem_desc_sw128(v_addr + st * kv_bytes + (uint32_t)s * 2048u, kv_block_bytes, 1024);
-          mma_ts(tm_o, tm_p + (uint32_t)s * 8u, db, idesc_pv, (j > 0) || (s > 0));
+          for (int s = 0; s < BN / 16; ++s) {
+            // B = V tile, MN-major: 64 head-dim elements contiguous (128 B) per key row, 8-row groups
+            // 1024 B apart (SBO), further 64-wide head-dim blocks kv_block_bytes apart (LBO).
+            const uint64_t db = make_smem_desc_sw128(v_addr + st * kv_bytes + (uint32_t)s * 2048u, kv_block_bytes, 1024);
+            mma_ts(tm_o, tm_p + (uint32_t)s * 8u, db, idesc_pv, (j > 0) || (s > 0));
+          }
+          tc_commit(&bars.v_empty[st]);
+          if (j + 1 < n_tiles) issue_qk(j + 1);            // in order behind PV_j: may overwrite P_j
+          else tc_commit(&bars.o_done);
         }
-        tc_commit(&bars.v_empty[st]);
-        tc_commit(&bars.o_done);
       }
     }
   } else {
     // =========================== softmax / correction / epilogue ================================
+    if (kMinBlocks >= 4) reg_inc<104>();
     const int quarter = warp & 3;                        // TMEM lane quarter this warp may touch
     const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
     const int row = q_tile * kBM + quarter * 32 + lane;  // query row owned by this thread
@@ -187,15 +199,13 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
       const int row0 = (seg2 ? j - t1 : j) * BN;
       const int valid = min(BN, (seg2 ? P.n_kv2 : P.n_kv) - row0);
 
+      // S_j complete; the commit also covers PV_{j-1}, so P/O are ours again.
       mbar_wait(&bars.s_full, (uint32_t)j & 1);
       tc_fence_after();
       uint32_t sr[BN / 32][32];
 #pragma unroll
       for (int c = 0; c < BN / 32; ++c) tmem_ld_x32(tm_s + lane_off + c * 32, sr[c]);
       tmem_wait_ld();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&bars.s_empty);
 
       if (valid < BN) {
 #pragma unroll
@@ -204,15 +214,18 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
           for (int i = 0; i < 32; ++i)
             if (c * 32 + i >= valid) sr[c][i] = 0xff800000u;   // -inf
       }
-      float mx0 = __uint_as_float(sr[0][0]), mx1 = __uint_as_float(sr[0][1]);
+      // row max: 3-input FMNMX3 in four independent chains
+      float mx[4];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) mx[t] = __uint_as_float(sr[0][t]);
 #pragma unroll
       for (int c = 0; c < BN / 32; ++c)
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          mx0 = fmaxf(mx0, __uint_as_float(sr[c][i]));
-          mx1 = fmaxf(mx1, __uint_as_float(sr[c][i + 1]));
-        }
-      const float cand = fmaxf(mx0, mx1) * P.scale_log2;
+        for (int i = 0; i < 32; i += 8)
+#pragma unroll
+          for (int t = 0; t < 4; ++t)
+            mx[t] = fmax3(mx[t], __uint_as_float(sr[c][i + 2 * t]), __uint_as_float(sr[c][i + 2 * t + 1]));
+      const float cand = fmaxf(fmax3(mx[0], mx[1], mx[2]), mx[3]) * P.scale_log2;
       float alpha = 1.0f;
       bool need = false;
       if (j == 0) {
@@ -222,13 +235,11 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         m_ref = cand;
         need = true;
       }
-      if (j > 0) {
-        // PV_{j-1} retired (it was issued before S_j was consumed, so this never stalls in steady
-        // state): the P columns and O are ours again.
-        mbar_wait(&bars.o_done, (uint32_t)(j - 1) & 1);
-        tc_fence_after();
-      }
-      float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f, sum3 = 0.f;
+      // p = exp2(s * c - m_ref): packed FFMA2 for the affine part, MUFU.EX2 per element, packed FADD2
+      // row sums in two independent chains, bf16x2 packing for the P operand.
+      const uint64_t c2 = pack2(P.scale_log2, P.scale_log2);
+      const uint64_t nm2 = pack2(-m_ref, -m_ref);
+      uint64_t acc_a = 0ull, acc_b = 0ull;     // (+0.0f, +0.0f)
 #pragma unroll
       for (int g = 0; g < BN / 64; ++g) {            // 64 score columns -> 32 packed bf16x2 columns
         uint32_t pk[32];
@@ -237,17 +248,34 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
 #pragma unroll
           for (int i = 0; i < 32; i += 4) {
             const int c = g * 2 + cc;
-            const float p0 = ex2_approx(fmaf(__uint_as_float(sr[c][i + 0]), P.scale_log2, -m_ref));
-            const float p1 = ex2_approx(fmaf(__uint_as_float(sr[c][i + 1]), P.scale_log2, -m_ref));
-            const float p2 = ex2_approx(fmaf(__uint_as_float(sr[c][i + 2]), P.scale_log2, -m_ref));
-            const float p3 = ex2_approx(fmaf(__uint_as_float(sr[c][i + 3]), P.scale_log2, -m_ref));
-            sum0 += p0; sum1 += p1; sum2 += p2; sum3 += p3;
+            const uint64_t xa = ffma2(pack2(__uint_as_float(sr[c][i + 0]), __uint_as_float(sr[c][i + 1])), c2, nm2);
+            const uint64_t xb = ffma2(pack2(__uint_as_float(sr[c][i + 2]), __uint_as_float(sr[c][i + 3])), c2, nm2);
+            float p0, p1, p2, p3;
+            if (((i / 2) & 3) < kEmu) {
+              exp2_poly2(xa, p0, p1);
+            } else {
+              float t0, t1;
+              unpack2(xa, t0, t1);
+              p0 = ex2_approx(t0); p1 = ex2_approx(t1);
+            }
+            if (((i / 2 + 1) & 3) < kEmu) {
+              exp2_poly2(xb, p2, p3);
+            } else {
+              float t2, t3;
+              unpack2(xb, t2, t3);
+              p2 = ex2_approx(t2); p3 = ex2_approx(t3);
+            }
+            acc_a = fadd2(acc_a, pack2(p0, p1));
+            acc_b = fadd2(acc_b, pack2(p2, p3));
             pk[cc * 16 + i / 2 + 0] = pack_bf16(p0, p1);
             pk[cc * 16 + i / 2 + 1] = pack_bf16(p2, p3);
           }
         tmem_st_x32(tm_p + lane_off + g * 32, pk);
       }
-      l = l * alpha + ((sum0 + sum1) + (sum2 + sum3));
+      float sa0, sa1, sb0, sb1;
+      unpack2(acc_a, sa0, sa1);
+      unpack2(acc_b, sb0, sb1);
+      l = l * alpha + ((sa0 + sa1) + (sb0 + sb1));
       if (j > 0 && __any_sync(0xffffffffu, need)) {
         for (int c = 0; c < P.d; c += 8) {
           uint32_t o8[8];
@@ -265,7 +293,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     }
 
     // ---- epilogue: O / l -> bf16 -> global ------------------------------------------------------
-    mbar_wait(&bars.o_done, (uint32_t)(n_tiles - 1) & 1);
+    mbar_wait(&bars.o_done, 0);
     tc_fence_after();
     const float inv_l = 1.0f / l;
     __nv_bfloat16* orow = P.o + ((long long)b * P.n_q + row) * P.ld_o + (long long)h * P.d;
@@ -324,17 +352,17 @@ static int make_map(CUtensorMap* m, const void* base, int batch, int heads, int 
   return 0;
 }
 
-template <int BN, int kTmemCols>
+template <int BN, int kTmemCols, int kMinBlocks, int kEmu>
 static int launch_tc(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const CUtensorMap& mk2,
                      const CUtensorMap& mv2, const AttnTcParams& P, int batch, cudaStream_t st) {
   const size_t smem = 1024 + (size_t)P.kb * (kBM * 128 + 4 * BN * 128);
   static bool attr = false;
   if (!attr) {
-    VF_CUDA_TRY(cudaFuncSetAttribute(attn_tc_kernel<BN, kTmemCols>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    VF_CUDA_TRY(cudaFuncSetAttribute(attn_tc_kernel<BN, kTmemCols, kMinBlocks, kEmu>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr = true;
   }
   dim3 grid((P.n_q + kBM - 1) / kBM, batch * P.heads);
-  attn_tc_kernel<BN, kTmemCols><<<grid, kTcThreads, smem, st>>>(mq, mk, mv, mk2, mv2, P);
+  attn_tc_kernel<BN, kTmemCols, kMinBlocks, kEmu><<<grid, kTcThreads, smem, st>>>(mq, mk, mv, mk2, mv2, P);
   return check_cuda(cudaGetLastError(), "attn_tc_kernel launch");
 }
 
@@ -362,7 +390,7 @@ int launch_attn_tc(const void* q, const void* k, const void* v, void* o, int bat
   P.heads = heads; P.n_q = n_q; P.n_kv = n_kv; P.n_kv2 = has2 ? n_kv2 : 0;
   P.d = d; P.d_pad = (d + 15) / 16 * 16; P.kb = (d + 63) / 64;
   P.scale_log2 = scale * 1.4426950408889634f;
-  const int bn = d <= 64 ? 128 : 64;
+  const int bn = 64;
   CUtensorMap mq, mk, mv, mk2, mv2;
   if (int rc = make_map(&mq, q, batch, heads, n_q, d, ld_q, kBM)) return rc;
   if (int rc = make_map(&mk, k, batch, heads, n_kv, d, ld_k, bn)) return rc;
@@ -374,9 +402,22 @@ int launch_attn_tc(const void* q, const void* k, const void* v, void* o, int bat
     mk2 = mk;
     mv2 = mv;
   }
-  if (bn == 128) return launch_tc<128, 256>(mq, mk, mv, mk2, mv2, P, batch, st);
-  if (64 + 32 + P.d_pad <= 256) return launch_tc<64, 256>(mq, mk, mv, mk2, mv2, P, batch, st);
-  return launch_tc<64, 512>(mq, mk, mv, mk2, mv2, P, batch, st);
+  // TMEM: BN S columns (P aliased) + d_pad O columns, rounded up to a power of two.
+  static int emu = -1;      // tuning knob: VF_ATTN_EMU = 0..3 pairs of every 4 on the FMA pipe
+  if (emu < 0) {
+    const char* e = getenv("VF_ATTN_EMU");
+    emu = e ? atoi(e) : 1;
+    if (emu < 0 || emu > 3) emu = 1;
+  }
+  if (P.d_pad <= 64) {                                                                   // 48 KB smem: 4 CTAs / SM
+    switch (emu) {
+      case 0: return launch_tc<64, 128, 4, 0>(mq, mk, mv, mk2, mv2, P, batch, st);
+      case 2: return launch_tc<64, 128, 4, 2>(mq, mk, mv, mk2, mv2, P, batch, st);
+      case 3: return launch_tc<64, 128, 4, 3>(mq, mk, mv, mk2, mv2, P, batch, st);
+      default: return launch_tc<64, 128, 4, 1>(mq, mk, mv, mk2, mv2, P, batch, st);
+    }
+  }
+  return launch_tc<64, 256, 2, 0>(mq, mk, mv, mk2, mv2, P, batch, st);                    // d in (64, 192]
 }
 
 }  // namespace vf

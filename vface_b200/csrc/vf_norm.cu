@@ -69,11 +69,12 @@ template <typename T, int CPT>    // CPT: chunks per thread along the channel ax
 __global__ void __launch_bounds__(kGnThreads)
 gn_stats_kernel(const GnParams P) {
   constexpr int E = V16<T>::E;
-  __shared__ float s_sum[kGnMaxGroups], s_sq[kGnMaxGroups];
+  // per-(row lane, channel) partials, reduced to groups in a fixed order: bit-reproducible statistics
+  extern __shared__ float s_part[];      // [2][rpb * c]
   const int n = blockIdx.y, slab = blockIdx.x;
-  if (threadIdx.x < kGnMaxGroups) { s_sum[threadIdx.x] = 0.f; s_sq[threadIdx.x] = 0.f; }
-  __syncthreads();
   const GnMap M(P.c, E);
+  float* s_psum = s_part;
+  float* s_psq = s_part + M.rpb * P.c;
   const int cpg = P.c / P.groups;
   const int r0 = slab * P.rows_per_slab;
   const int r1 = min(P.hw, r0 + P.rows_per_slab);
@@ -106,18 +107,23 @@ gn_stats_kernel(const GnParams P) {
       if (ch < P.c) {
 #pragma unroll
         for (int j = 0; j < E; ++j) {
-          const int g = (ch + j) / cpg;
-          atomicAdd(&s_sum[g], sum[k][j]);
-          atomicAdd(&s_sq[g], sq[k][j]);
+          s_psum[M.my_row * P.c + ch + j] = sum[k][j];
+          s_psq[M.my_row * P.c + ch + j] = sq[k][j];
         }
       }
     }
   }
   __syncthreads();
   if (threadIdx.x < P.groups) {
+    float gs = 0.f, gq = 0.f;
+    for (int r = 0; r < M.rpb; ++r)
+      for (int ch = threadIdx.x * cpg; ch < (threadIdx.x + 1) * cpg; ++ch) {
+        gs += s_psum[r * P.c + ch];
+        gq += s_psq[r * P.c + ch];
+      }
     float* w = P.ws + (((size_t)n * P.slabs + slab) * P.groups + threadIdx.x) * 2;
-    w[0] = s_sum[threadIdx.x];
-    w[1] = s_sq[threadIdx.x];
+    w[0] = gs;
+    w[1] = gq;
   }
 }
 
@@ -376,9 +382,13 @@ extern "C" int vf_group_norm_nhwc(const void* x, const void* add_nc, const void*
   dim3 grid(P.slabs, n);
   cudaStream_t st = (cudaStream_t)stream;
   const int cpt = (c / e + kGnThreads - 1) / kGnThreads;
+  const int chunks_ = c / e;
+  const int rpb_ = kGnThreads / (chunks_ < kGnThreads ? chunks_ : kGnThreads);
+  const size_t stats_smem = (size_t)2 * rpb_ * c * sizeof(float);
+  if (stats_smem > 48 * 1024) return fail("vf_group_norm_nhwc: c=%d too wide", c);
 #define VF_GN_LAUNCH(T, K)                                        \
   do {                                                            \
-    gn_stats_kernel<T, K><<<grid, kGnThreads, 0, st>>>(P);        \
+    gn_stats_kernel<T, K><<<grid, kGnThreads, stats_smem, st>>>(P);        \
     gn_apply_kernel<T, K><<<grid, kGnThreads, 0, st>>>(P);        \
   } while (0)
   if (dtype == VF_F32) {

@@ -34,9 +34,9 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+      : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u) : "memory");   // suspend-time hint: sleep in HW, do not spin
   return ok != 0;
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
@@ -155,6 +155,55 @@ __device__ __forceinline__ void tmem_st_x8(uint32_t taddr, const uint32_t (&r)[8
       "tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
       :: "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
       : "memory");
+}
+
+// ---- packed fp32x2 / 3-input ALU ops (new on sm_100) ------------------------------------------------
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t pack2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+
+// 2^x for a pair on the FMA pipe instead of MUFU (Cody-Waite split + degree-3 minimax polynomial,
+// max relative error 7.5e-5, far below the bf16 rounding of P).  x must be <= ~100; it is clamped
+// below at -126 (result 2^-126, which rounds to 0 in the bf16 P operand's contribution).
+__device__ __forceinline__ void exp2_poly2(uint64_t x2, float& r0, float& r1) {
+  float x0, x1;
+  unpack2(x2, x0, x1);
+  x0 = fmaxf(x0, -126.0f);
+  x1 = fmaxf(x1, -126.0f);
+  const uint64_t xc = pack2(x0, x1);
+  const uint64_t magic = pack2(12582912.0f, 12582912.0f);              // 1.5 * 2^23
+  const uint64_t t2 = fadd2(xc, magic);                                // low mantissa bits = rint(x)
+  const uint64_t r2 = fadd2(t2, pack2(-12582912.0f, -12582912.0f));    // rint(x) as float
+  const uint64_t f2 = ffma2(r2, pack2(-1.0f, -1.0f), xc);              // f = x - rint(x) in [-0.5, 0.5]
+  uint64_t p2 = ffma2(f2, pack2(5.517163806e-02f, 5.517163806e-02f), pack2(2.426111198e-01f, 2.426111198e-01f));
+  p2 = ffma2(p2, f2, pack2(6.932609912e-01f, 6.932609912e-01f));
+  p2 = ffma2(p2, f2, pack2(9.999280738e-01f, 9.999280738e-01f));
+  float p0, p1, t0, t1;
+  unpack2(p2, p0, p1);
+  unpack2(t2, t0, t1);
+  // scale by 2^rint(x): add rint(x) to the exponent field (the magic's own bits shift out)
+  r0 = __uint_as_float(__float_as_uint(p0) + (__float_as_uint(t0) << 23));
+  r1 = __uint_as_float(__float_as_uint(p1) + (__float_as_uint(t1) << 23));
 }
 
 __device__ __forceinline__ float ex2_approx(float x) {
