@@ -1,0 +1,69 @@
+"""D1: frame-sharded sampling == unsharded sampling.
+
+The driver's GPU box may expose a single device, so the two ranks are emulated one after the other
+on cuda:0 with a FrameShard whose halo exchange replays what rank 0 would have sent over NCCL (the
+real NCCL path is exercised by `bench.py --gpus 2`; the gloo path by tests/test_host_logic.py).
+Shard assignment is bit-exact by construction (shard_bounds); latents agree to fp32 round-off
+(cuBLAS/cuDNN pick batch-size-dependent kernels, so bitwise equality across batch sizes is not defined).
+"""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+SMALL = dict(model_channels=32, num_heads=2)
+
+
+class ReplayShard:
+    """FrameShard stand-in: rank 0 records its halo sends, rank 1 replays them in order."""
+
+    def __init__(self, rank, world, total, tape):
+        from vface_b200.frame_shard import FrameShard
+        self._fs = FrameShard(rank, world, total)
+        self.rank, self.world_size, self.total_frames = rank, world, total
+        self.lo, self.hi = self._fs.lo, self._fs.hi
+        self.tape = tape
+        self.pos = 0
+
+    def take(self, t):
+        return self._fs.take(t)
+
+    def local_flow(self, flow):
+        return self._fs.local_flow(flow)
+
+    def exchange_halo(self, q_last, k_last):
+        if self.rank == 0:
+            self.tape.append((q_last.clone(), k_last.clone()))
+            return None, None
+        q, k = self.tape[self.pos]
+        self.pos += 1
+        return q, k
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-5), (torch.bfloat16, 1e-2)])
+def test_two_shards_equal_unsharded(dtype, tol):
+    from oracle import kernels as ok
+    from tests.test_pipeline_gpu import build, rel_l2, run_sample
+    from vface_b200 import frame_shard, synth
+    S, F = 4, 4
+    steps = ok.make_schedule(S)["ddim_timesteps"]
+    clip = synth.synth_clip(F, steps=steps)
+    _, sampler, _ = build(SMALL, dtype)
+    frame_shard.activate(None)
+    full, _ = run_sample(sampler, clip, S, F, clip["inversion"])
+
+    tape, parts = [], []
+    try:
+        for rank in range(2):
+            sh = ReplayShard(rank, 2, F, tape)
+            frame_shard.activate(sh)
+            local = {k: (sh.take(v) if isinstance(v, torch.Tensor) else v) for k, v in clip.items()}
+            local["flow"] = sh.local_flow(clip["flow"])
+            inv = {t: sh.take(v) for t, v in clip["inversion"].items()}
+            out, _ = run_sample(sampler, local, S, sh.hi - sh.lo, inv, flow=local["flow"])
+            parts.append(out)
+    finally:
+        frame_shard.activate(None)
+    # 2 flow-active modules x (q,k packed in one message) x S steps
+    assert len(tape) == 2 * S
+    assert rel_l2(torch.cat(parts), full) < tol
