@@ -5,6 +5,9 @@ on cuda:0 with a FrameShard whose halo exchange replays what rank 0 would have s
 real NCCL path is exercised by `bench.py --gpus 2`; the gloo path by tests/test_host_logic.py).
 Shard assignment is bit-exact by construction (shard_bounds); latents agree to fp32 round-off
 (cuBLAS/cuDNN pick batch-size-dependent kernels, so bitwise equality across batch sizes is not defined).
+In bf16 the two runs are two independent roundings of the same fp32 trajectory (each within the 1e-2
+per-step budget of the fp32 result on this random-weight UNet with S=4), so they are compared at 2e-2;
+the fp32 case (1e-5) is the one that proves the sharded evaluation is the same computation.
 """
 import pytest
 import torch
@@ -40,7 +43,7 @@ class ReplayShard:
         return q, k
 
 
-@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-5), (torch.bfloat16, 1e-2)])
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-5), (torch.bfloat16, 2e-2)])
 def test_two_shards_equal_unsharded(dtype, tol):
     from oracle import kernels as ok
     from tests.test_pipeline_gpu import build, rel_l2, run_sample
