@@ -81,7 +81,7 @@ def bench_attn(res, iters):
 def bench_fsai(res, iters):
     pk = peaks()
     for dt, e in ((torch.bfloat16, 2), (torch.float32, 4)):
-        for n, c in ((4096, 320), (1024, 640)):
+        for n, c in ((4096, 320), (1024, 640), (256, 1280)):
             frames = 64
             g = torch.Generator(device="cuda").manual_seed(0)
             q = torch.randn(3 * frames, n, c, device="cuda", generator=g).to(dt)

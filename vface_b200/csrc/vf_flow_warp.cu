@@ -70,69 +70,123 @@ template <> struct Chunk<__nv_bfloat16> {
   }
 };
 
-// One thread = one 16-byte channel chunk of one output pixel.  Frame 0 without a halo is a copy.
+// ---- blend arithmetic on one 16-byte chunk ----------------------------------------------------------
+// Values follow grid_sample's tap order (nw, ne, sw, se) and temporal_flow.py:234 with fused
+// multiply-adds (packed FFMA2): within 1 ulp of the reference's separate mul/add chain; only the tap
+// INDEX chain above has to be (and is) bit-exact.
+struct Wts {
+  float nw, ne, sw, se;
+};
+
 template <typename T>
-__global__ void __launch_bounds__(256)
+__device__ __forceinline__ uint4 blend_chunk(const uint4& cu, const uint4& u_nw, const uint4& u_ne, const uint4& u_sw,
+                                              const uint4& u_se, const Wts& wt, float alpha, float one_minus_alpha) {
+  constexpr int E = Chunk<T>::kElems;
+  float c[E], a[E], b[E], s[E], d[E], o[E];
+  Chunk<T>::unpack(cu, c);
+  Chunk<T>::unpack(u_nw, a);
+  Chunk<T>::unpack(u_ne, b);
+  Chunk<T>::unpack(u_sw, s);
+  Chunk<T>::unpack(u_se, d);
+#pragma unroll
+  for (int j = 0; j < E; j += 2) {
+    float2 acc = __fmul2_rn(make_float2(a[j], a[j + 1]), make_float2(wt.nw, wt.nw));
+    acc = __ffma2_rn(make_float2(b[j], b[j + 1]), make_float2(wt.ne, wt.ne), acc);
+    acc = __ffma2_rn(make_float2(s[j], s[j + 1]), make_float2(wt.sw, wt.sw), acc);
+    acc = __ffma2_rn(make_float2(d[j], d[j + 1]), make_float2(wt.se, wt.se), acc);
+    const float2 ac = __fmul2_rn(make_float2(c[j], c[j + 1]), make_float2(alpha, alpha));
+    const float2 r = __ffma2_rn(acc, make_float2(one_minus_alpha, one_minus_alpha), ac);
+    o[j] = r.x;
+    o[j + 1] = r.y;
+  }
+  return Chunk<T>::pack(o);
+}
+
+// One CTA iteration = one 8x8 pixel tile of one frame.  The 64 pixels' taps (four source-pixel indices
+// + four weights) are computed ONCE by 64 threads into shared memory -- the index chain costs ~100
+// instructions (two IEEE divisions per axis) and used to be repeated by every 16-byte chunk of the
+// pixel (40x at C=320 bf16), which made the kernel issue-bound.  Then 8 lanes per pixel stream the
+// channel chunks: 128-byte segments per tap row, the 2-D tile keeps the gathered rows L1/L2-resident.
+constexpr int kWarpThreads = 256;
+constexpr int kTile = 8;
+constexpr int kLanesPerPx = 8;
+
+template <typename T>
+__global__ void __launch_bounds__(kWarpThreads)
 flow_warp_blend_kernel(const T* __restrict__ x, const T* __restrict__ halo, const float* __restrict__ flow,
                        T* __restrict__ out, int* __restrict__ taps_out,
                        int frames, int h, int w, int chunks_per_px,
                        long long ld_x, long long ld_halo, long long ld_out, float alpha, float one_minus_alpha) {
   constexpr int E = Chunk<T>::kElems;
+  __shared__ int4 s_off[kTile * kTile];
+  __shared__ float4 s_wt[kTile * kTile];
   const int npx = h * w;
-  const long long per_frame = (long long)npx * chunks_per_px;
-  const long long total = per_frame * frames;
+  const int tiles_x = (w + kTile - 1) / kTile, tiles_y = (h + kTile - 1) / kTile;
+  const int tiles_per_frame = tiles_x * tiles_y;
+  const long long n_tiles = (long long)tiles_per_frame * frames;
   const bool has_halo = halo != nullptr;
-  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x) {
-    int f = (int)(idx / per_frame);
-    long long rem = idx - (long long)f * per_frame;
-    int p = (int)(rem / chunks_per_px);
-    int ch = (int)(rem - (long long)p * chunks_per_px);
-    const T* cur = x + ((long long)f * npx + p) * ld_x + ch * E;
-    T* dst = out + ((long long)f * npx + p) * ld_out + ch * E;
-    uint4 cu = ld_nc_v4(cur);
-    if (f == 0 && !has_halo) {   // out[0] = x[0]   (temporal_flow.py:229, clone)
-      st_na_v4(dst, cu);
-      continue;
-    }
+  const int cl = threadIdx.x & (kLanesPerPx - 1);
+  const int ps = threadIdx.x / kLanesPerPx;                  // 0..31
+
+  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int f = (int)(tile / tiles_per_frame);
+    const int tr = (int)(tile - (long long)f * tiles_per_frame);
+    const int ty0 = (tr / tiles_x) * kTile, tx0 = (tr % tiles_x) * kTile;
+    const bool copy_only = (f == 0 && !has_halo);            // out[0] = x[0] (temporal_flow.py:229)
     const int fl = has_halo ? f : f - 1;
-    const float* fp = flow + (long long)fl * 2 * npx;
-    const int py = p / w, px = p - py * w;
-    Taps t = make_taps(px, py, __ldg(fp + p), __ldg(fp + npx + p), h, w);
-    if (taps_out != nullptr && ch == 0) {
-      taps_out[((long long)fl * npx + p) * 2 + 0] = t.x0;
-      taps_out[((long long)fl * npx + p) * 2 + 1] = t.y0;
+    if (!copy_only && threadIdx.x < kTile * kTile) {
+      const int py = ty0 + (threadIdx.x >> 3), px = tx0 + (threadIdx.x & 7);
+      if (py < h && px < w) {
+        const int p = py * w + px;
+        const float* fp = flow + (long long)fl * 2 * npx;
+        const Taps t = make_taps(px, py, __ldg(fp + p), __ldg(fp + npx + p), h, w);
+        if (taps_out != nullptr) {
+          taps_out[((long long)fl * npx + p) * 2 + 0] = t.x0;
+          taps_out[((long long)fl * npx + p) * 2 + 1] = t.y0;
+        }
+        const int x1 = t.in_x ? t.x0 + 1 : t.x0, y1 = t.in_y ? t.y0 + 1 : t.y0;
+        s_off[threadIdx.x] = make_int4(t.y0 * w + t.x0, t.y0 * w + x1, y1 * w + t.x0, y1 * w + x1);
+        s_wt[threadIdx.x] = make_float4(t.w_nw, t.in_x ? t.w_ne : 0.0f, t.in_y ? t.w_sw : 0.0f,
+                                        (t.in_x && t.in_y) ? t.w_se : 0.0f);
+      }
     }
+    __syncthreads();
     const T* prev;
     long long ldp;
     if (f == 0) { prev = halo; ldp = ld_halo; }
     else        { prev = x + (long long)(f - 1) * npx * ld_x; ldp = ld_x; }
-    prev += ch * E;
-    const int x1 = t.in_x ? t.x0 + 1 : t.x0, y1 = t.in_y ? t.y0 + 1 : t.y0;
-    // Gathered rows are re-read by neighbouring pixels: default (cached) loads.
-    uint4 u_nw = *reinterpret_cast<const uint4*>(prev + (long long)(t.y0 * w + t.x0) * ldp);
-    uint4 u_ne = *reinterpret_cast<const uint4*>(prev + (long long)(t.y0 * w + x1) * ldp);
-    uint4 u_sw = *reinterpret_cast<const uint4*>(prev + (long long)(y1 * w + t.x0) * ldp);
-    uint4 u_se = *reinterpret_cast<const uint4*>(prev + (long long)(y1 * w + x1) * ldp);
-    float c[E], a[E], b[E], s[E], d[E], o[E];
-    Chunk<T>::unpack(cu, c);
-    Chunk<T>::unpack(u_nw, a);
-    Chunk<T>::unpack(u_ne, b);
-    Chunk<T>::unpack(u_sw, s);
-    Chunk<T>::unpack(u_se, d);
-    const float w_ne = t.in_x ? t.w_ne : 0.0f;
-    const float w_sw = t.in_y ? t.w_sw : 0.0f;
-    const float w_se = (t.in_x && t.in_y) ? t.w_se : 0.0f;
 #pragma unroll
-    for (int j = 0; j < E; ++j) {
-      float acc = __fmul_rn(a[j], t.w_nw);
-      acc = __fadd_rn(acc, __fmul_rn(b[j], w_ne));
-      acc = __fadd_rn(acc, __fmul_rn(s[j], w_sw));
-      acc = __fadd_rn(acc, __fmul_rn(d[j], w_se));
-      // alpha * x[i+1] + (1 - alpha) * warped   (temporal_flow.py:234)
-      o[j] = __fadd_rn(__fmul_rn(alpha, c[j]), __fmul_rn(one_minus_alpha, acc));
+    for (int half = 0; half < 2; ++half) {
+      const int tp = ps + half * 32;
+      const int py = ty0 + (tp >> 3), px = tx0 + (tp & 7);
+      if (py >= h || px >= w) continue;
+      const long long p = (long long)f * npx + py * w + px;
+      const T* cur = x + p * ld_x;
+      T* dst = out + p * ld_out;
+      if (copy_only) {
+        for (int ch = cl; ch < chunks_per_px; ch += kLanesPerPx) st_na_v4(dst + ch * E, ld_nc_v4(cur + ch * E));
+        continue;
+      }
+      const int4 off = s_off[tp];
+      const float4 wq = s_wt[tp];
+      const Wts wt{wq.x, wq.y, wq.z, wq.w};
+      const T* r_nw = prev + (long long)off.x * ldp;
+      const T* r_ne = prev + (long long)off.y * ldp;
+      const T* r_sw = prev + (long long)off.z * ldp;
+      const T* r_se = prev + (long long)off.w * ldp;
+#pragma unroll 2
+      for (int ch = cl; ch < chunks_per_px; ch += kLanesPerPx) {
+        const int e0 = ch * E;
+        const uint4 cu = ld_nc_v4(cur + e0);
+        // gathered rows are re-read by neighbouring pixels: default (cached) loads
+        const uint4 u_nw = *reinterpret_cast<const uint4*>(r_nw + e0);
+        const uint4 u_ne = *reinterpret_cast<const uint4*>(r_ne + e0);
+        const uint4 u_sw = *reinterpret_cast<const uint4*>(r_sw + e0);
+        const uint4 u_se = *reinterpret_cast<const uint4*>(r_se + e0);
+        st_na_v4(dst + e0, blend_chunk<T>(cu, u_nw, u_ne, u_sw, u_se, wt, alpha, one_minus_alpha));
+      }
     }
-    st_na_v4(dst, Chunk<T>::pack(o));
+    __syncthreads();
   }
 }
 
@@ -158,18 +212,17 @@ extern "C" int vf_flow_warp_blend(const void* x, const void* prev_halo, const fl
       (prev_halo && (reinterpret_cast<uintptr_t>(prev_halo) & 15)))
     return fail("vf_flow_warp_blend: pointers must be 16-byte aligned");
   const int cpp = c / epc;
-  const long long total = (long long)frames * h * w * cpp;
-  long long blocks = (total + 255) / 256;
-  const long long cap = (long long)num_sms() * 16;
+  long long blocks = (long long)frames * ((h + vf::kTile - 1) / vf::kTile) * ((w + vf::kTile - 1) / vf::kTile);
+  const long long cap = (long long)num_sms() * 8;
   if (blocks > cap) blocks = cap;
   const float a = (float)alpha;
   const float b = (float)(1.0 - alpha);   // python: (1 - alpha) in double, cast to fp32 by the tensor op
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == VF_F32)
-    flow_warp_blend_kernel<float><<<(int)blocks, 256, 0, st>>>((const float*)x, (const float*)prev_halo, flow, (float*)out,
+    flow_warp_blend_kernel<float><<<(int)blocks, kWarpThreads, 0, st>>>((const float*)x, (const float*)prev_halo, flow, (float*)out,
                                                                taps_out, frames, h, w, cpp, ld_x, ld_halo, ld_out, a, b);
   else
-    flow_warp_blend_kernel<__nv_bfloat16><<<(int)blocks, 256, 0, st>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)prev_halo, flow,
+    flow_warp_blend_kernel<__nv_bfloat16><<<(int)blocks, kWarpThreads, 0, st>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)prev_halo, flow,
                                                                        (__nv_bfloat16*)out, taps_out, frames, h, w, cpp,
                                                                        ld_x, ld_halo, ld_out, a, b);
   return check_cuda(cudaGetLastError(), "flow_warp_blend_kernel launch");

@@ -19,6 +19,9 @@
 // HBM roofline: algorithmic bytes per row pair = 6*d*e (single) / 5*d*e (fused).
 #include "vf_common.cuh"
 
+#include <cstdlib>
+#include "vf_fsai_fast.cuh"
+
 namespace vf {
 
 constexpr int kFsaiThreads = 256;
@@ -267,6 +270,72 @@ fsai_kernel(const FsaiParams P) {
   }
 }
 
+// ---- fast path (vf_fsai_fast.cuh): the three channel widths of the REFace UNet ---------------------------
+template <typename C, int kMinBlocks>
+__global__ void __launch_bounds__(C::kThreads, kMinBlocks)
+fsai_fast_kernel(const fsaifast::Args A) {
+  extern __shared__ __align__(16) float sm_fast[];
+  float* sm_exch = sm_fast;
+  float* sm_tw1 = sm_exch + C::kExchFloats;
+  float* sm_rec = sm_tw1 + C::kTw1Floats;
+  {
+    float2* pre = reinterpret_cast<float2*>(sm_exch);          // W_D^j, only needed to fill the tables
+    static_assert(C::D * 2 <= C::kExchFloats, "scratch for the twiddle seed table");
+    for (int j = threadIdx.x; j < C::D; j += C::kThreads) {
+      float s, c;
+      sincospif(-2.0f * (float)j / (float)C::D, &s, &c);
+      pre[j] = make_float2(c, s);
+    }
+    __syncthreads();
+    constexpr int kItems = C::L * C::M > C::kSub ? C::L * C::M : C::kSub;
+    for (int i = threadIdx.x; i < kItems; i += C::kThreads) fsaifast::build_tables<C>(i, sm_tw1, sm_rec, pre, A.split);
+    __syncthreads();
+  }
+  const long long stride = (long long)gridDim.x * C::RP;
+  for (long long base = (long long)blockIdx.x * C::RP; base < A.n_pairs; base += stride) {
+    fsaifast::phase_a<C>(A, base, threadIdx.x, sm_exch, sm_tw1);
+    __syncthreads();
+    fsaifast::phase_b<C>(threadIdx.x, sm_exch, sm_rec);
+    __syncthreads();
+    fsaifast::phase_c<C>(A, base, threadIdx.x, sm_exch, sm_tw1);
+    __syncthreads();
+  }
+}
+
+template <typename C, int kMinBlocks>
+static int launch_fast(const FsaiParams& P, cudaStream_t st) {
+  fsaifast::Args A{};
+  A.donor = P.donor; A.dst_a = P.dst_a; A.out_a = P.out_a; A.dst_b = P.dst_b; A.out_b = P.out_b;
+  A.rows = P.rows; A.fused = P.fused;
+  A.n_pairs = P.fused ? P.rows : (P.rows + 1) / 2;
+  A.ld_donor = P.ld_donor; A.ld_a = P.ld_a; A.ld_out_a = P.ld_out_a; A.ld_b = P.ld_b; A.ld_out_b = P.ld_out_b;
+  A.split = P.split;
+  constexpr size_t smem = (size_t)C::kSmemFloats * sizeof(float);
+  static int blocks_per_sm = 0;
+  if (blocks_per_sm == 0) {
+    VF_CUDA_TRY(cudaFuncSetAttribute(fsai_fast_kernel<C, kMinBlocks>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int nb = 0;
+    VF_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fsai_fast_kernel<C, kMinBlocks>, C::kThreads, smem));
+    blocks_per_sm = nb > 0 ? nb : 1;
+  }
+  const long long iters = (A.n_pairs + C::RP - 1) / C::RP;
+  long long grid = (long long)num_sms() * blocks_per_sm;
+  if (grid > iters) grid = iters;
+  fsai_fast_kernel<C, kMinBlocks><<<(int)grid, C::kThreads, smem, st>>>(A);
+  return check_cuda(cudaGetLastError(), "fsai_fast_kernel launch");
+}
+
+template <typename T>
+static int dispatch_fast(const FsaiParams& P, cudaStream_t st, bool* handled) {
+  *handled = true;
+  switch (P.d) {
+    case 320: return launch_fast<fsaifast::Cfg<T, 320, 4, 10, 8, 16>, 3>(P, st);
+    case 640: return launch_fast<fsaifast::Cfg<T, 640, 2, 20, 16, 8>, 3>(P, st);
+    case 1280: return launch_fast<fsaifast::Cfg<T, 1280, 2, 20, 32, 8>, 1>(P, st);
+    default: *handled = false; return 0;
+  }
+}
+
 static int factor_radices(int d, int* radix) {
   int n = 0, r = d;
   while (r % 5 == 0) { if (n == kMaxStages) return -1; radix[n++] = 5; r /= 5; }
@@ -292,6 +361,11 @@ static int launch_fsai(FsaiParams& P, int dtype, cudaStream_t st, const char* wh
   for (const void* q : ptrs) {
     if (!q) return fail("%s: null pointer", who);
     if (reinterpret_cast<uintptr_t>(q) & 15) return fail("%s: pointers must be 16-byte aligned", who);
+  }
+  if (!getenv("VF_FSAI_GENERIC")) {
+    bool handled = false;
+    const int rc = dtype == VF_F32 ? dispatch_fast<float>(P, st, &handled) : dispatch_fast<__nv_bfloat16>(P, st, &handled);
+    if (handled) return rc;
   }
   int ppb = 5120 / P.d;
   if (ppb < 1) ppb = 1;
