@@ -48,12 +48,15 @@ struct AttnTcParams {
   float scale_log2;                            // scale * log2(e)
 };
 
+constexpr int kMaxStages = 4;
+
 struct __align__(8) TcBarriers {
   uint64_t q_full;
-  uint64_t k_full[2], k_empty[2];
-  uint64_t v_full[2], v_empty[2];
+  uint64_t k_full[kMaxStages], k_empty[kMaxStages];
+  uint64_t v_full[kMaxStages], v_empty[kMaxStages];
   uint64_t s_full, p_full, o_done;
-  uint32_t tmem_base;
+  uint64_t s_free, p_empty;          // kSplitP only
+  uint32_t tmem_base, tmem_base_p;
 };
 
 template <int kRegs> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" :: "n"(kRegs)); }
@@ -62,7 +65,11 @@ template <int kRegs> __device__ __forceinline__ void reg_inc() { asm volatile("s
 // kMinBlocks CTAs per SM; with 4 the launch-time register budget is 64 per thread and the softmax
 // warpgroup is raised to 104 with the 40 that warpgroup 0 gives up.
 // kEmu of every 4 score pairs take their exp2 on the FMA pipe (polynomial) instead of MUFU.
-template <int BN, int kTmemCols, int kMinBlocks, int kEmu>
+// kSplitP: P lives in its own 32-column TMEM allocation instead of aliasing S.  S_j is then free as soon
+// as the softmax threads have loaded it into registers (s_free), so QK_{j+1} is issued while softmax_j is
+// still in its exponentials and the softmax warps never wait for the tensor pipe; PV_j follows when P_j is
+// complete (p_full) and releases P with its own commit (p_empty).  160 TMEM columns -> three CTAs per SM.
+template <int BN, int kTmemCols, int kMinBlocks, int kEmu, bool kSplitP, int kStages>
 __global__ void __launch_bounds__(kTcThreads, kMinBlocks)
 attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                const __grid_constant__ CUtensorMap map_v, const __grid_constant__ CUtensorMap map_k2,
@@ -85,8 +92,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
   const uint32_t q_bytes = P.kb * q_block_bytes;
   const uint32_t kv_bytes = P.kb * kv_block_bytes;
   unsigned char* sQ = tiles;
-  unsigned char* sK = sQ + q_bytes;                 // 2 stages
-  unsigned char* sV = sK + 2 * kv_bytes;            // 2 stages
+  unsigned char* sK = sQ + q_bytes;                 // kStages stages
+  unsigned char* sV = sK + kStages * kv_bytes;      // kStages stages
 
   const int t1 = (P.n_kv + BN - 1) / BN;
   const int t2 = (P.n_kv2 + BN - 1) / BN;
@@ -94,7 +101,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
 
   if (threadIdx.x == 0) {
     mbar_init(&bars.q_full, 1);
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < kStages; ++s) {
       mbar_init(&bars.k_full[s], 1);
       mbar_init(&bars.k_empty[s], 1);
       mbar_init(&bars.v_full[s], 1);
@@ -103,19 +110,29 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     mbar_init(&bars.s_full, 1);
     mbar_init(&bars.p_full, 4);
     mbar_init(&bars.o_done, 1);
+    mbar_init(&bars.s_free, 4);
+    mbar_init(&bars.p_empty, 1);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc<kTmemCols>(&bars.tmem_base);
+  if (warp == 1) {
+    if (kSplitP) {
+      tmem_alloc_only<kTmemCols>(&bars.tmem_base);
+      tmem_alloc_only<BN / 2>(&bars.tmem_base_p);
+      tmem_relinquish();
+    } else {
+      tmem_alloc<kTmemCols>(&bars.tmem_base);
+    }
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = bars.tmem_base;
   const uint32_t tm_s = tmem;          // S (fp32, BN columns); P (bf16x2) overwrites its first BN/2 columns
-  const uint32_t tm_p = tmem;
+  const uint32_t tm_p = kSplitP ? bars.tmem_base_p : tmem;
   const uint32_t tm_o = tmem + BN;
 
   if (warp < 4) {
-    if (kMinBlocks >= 4) reg_dec<24>();
+    if (kMinBlocks >= 3) reg_dec<24>();
     if (warp == 0) {
       // =========================== TMA producer ==================================================
       if (lane == 0) {
@@ -126,8 +143,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         for (int kb = 0; kb < P.kb; ++kb)
           tma_load_4d(sQ + kb * q_block_bytes, &map_q, &bars.q_full, kb * 64, h, q_tile * kBM, b);
         for (int j = 0; j < n_tiles; ++j) {
-          const int st = j & 1;
-          const uint32_t use = (uint32_t)(j >> 1);
+          const int st = j % kStages;
+          const uint32_t use = (uint32_t)(j / kStages);
           const bool seg2 = j >= t1;
           const int row0 = (seg2 ? j - t1 : j) * BN;
           const CUtensorMap* mk = seg2 ? &map_k2 : &map_k;
@@ -153,8 +170,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         const uint32_t v_addr = smem_u32(sV);
 
         auto issue_qk = [&](int j) {
-          const int st = j & 1;
-          mbar_wait(&bars.k_full[st], (uint32_t)(j >> 1) & 1);
+          const int st = j % kStages;
+          mbar_wait(&bars.k_full[st], (uint32_t)(j / kStages) & 1);
           tc_fence_after();
           for (int s = 0; s < k_steps; ++s) {
             const uint32_t off_blk = (uint32_t)(s >> 2), off_in = (uint32_t)(s & 3) * 32u;
@@ -169,8 +186,13 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         mbar_wait(&bars.q_full, 0);
         issue_qk(0);
         for (int j = 0; j < n_tiles; ++j) {
-          const int st = j & 1;
-          mbar_wait(&bars.v_full[st], (uint32_t)(j >> 1) & 1);
+          const int st = j % kStages;
+          if (kSplitP && j + 1 < n_tiles) {
+            mbar_wait(&bars.s_free, (uint32_t)j & 1);      // S_j is in the softmax threads' registers
+            tc_fence_after();
+            issue_qk(j + 1);
+          }
+          mbar_wait(&bars.v_full[st], (uint32_t)(j / kStages) & 1);
           mbar_wait(&bars.p_full, (uint32_t)j & 1);        // P_j in TMEM (over S_j), O rescaled if needed
           tc_fence_after();
 #pragma unroll 1
@@ -181,14 +203,20 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
             mma_ts(tm_o, tm_p + (uint32_t)s * 8u, db, idesc_pv, (j > 0) || (s > 0));
           }
           tc_commit(&bars.v_empty[st]);
-          if (j + 1 < n_tiles) issue_qk(j + 1);            // in order behind PV_j: may overwrite P_j
-          else tc_commit(&bars.o_done);
+          if (kSplitP) {
+            tc_commit(&bars.p_empty);
+            if (j + 1 == n_tiles) tc_commit(&bars.o_done);
+          } else {
+            if (j + 1 < n_tiles) issue_qk(j + 1);          // in order behind PV_j: may overwrite P_j
+            else tc_commit(&bars.o_done);
+          }
         }
       }
     }
   } else {
     // =========================== softmax / correction / epilogue ================================
     if (kMinBlocks >= 4) reg_inc<104>();
+    else if (kMinBlocks == 3) reg_inc<136>();
     const int quarter = warp & 3;                        // TMEM lane quarter this warp may touch
     const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
     const int row = q_tile * kBM + quarter * 32 + lane;  // query row owned by this thread
@@ -206,6 +234,11 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
 #pragma unroll
       for (int c = 0; c < BN / 32; ++c) tmem_ld_x32(tm_s + lane_off + c * 32, sr[c]);
       tmem_wait_ld();
+      if (kSplitP) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars.s_free);
+      }
 
       if (valid < BN) {
 #pragma unroll
@@ -270,6 +303,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
             pk[cc * 16 + i / 2 + 0] = pack_bf16(p0, p1);
             pk[cc * 16 + i / 2 + 1] = pack_bf16(p2, p3);
           }
+        if (kSplitP && g == 0 && j > 0) {              // PV_{j-1} still reads P (and writes O) until its commit
+          mbar_wait(&bars.p_empty, (uint32_t)(j - 1) & 1);
+          tc_fence_after();
+        }
         tmem_st_x32(tm_p + lane_off + g * 32, pk);
       }
       float sa0, sa1, sb0, sb1;
@@ -317,6 +354,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc<kTmemCols>(tmem);
+    if (kSplitP) tmem_dealloc<BN / 2>(bars.tmem_base_p);
   }
 }
 
@@ -352,17 +390,17 @@ static int make_map(CUtensorMap* m, const void* base, int batch, int heads, int 
   return 0;
 }
 
-template <int BN, int kTmemCols, int kMinBlocks, int kEmu>
+template <int BN, int kTmemCols, int kMinBlocks, int kEmu, bool kSplitP = false, int kStages = 2>
 static int launch_tc(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const CUtensorMap& mk2,
                      const CUtensorMap& mv2, const AttnTcParams& P, int batch, cudaStream_t st) {
-  const size_t smem = 1024 + (size_t)P.kb * (kBM * 128 + 4 * BN * 128);
+  const size_t smem = 1024 + (size_t)P.kb * (kBM * 128 + 2 * kStages * BN * 128);
   static bool attr = false;
   if (!attr) {
-    VF_CUDA_TRY(cudaFuncSetAttribute(attn_tc_kernel<BN, kTmemCols, kMinBlocks, kEmu>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    VF_CUDA_TRY(cudaFuncSetAttribute(attn_tc_kernel<BN, kTmemCols, kMinBlocks, kEmu, kSplitP, kStages>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr = true;
   }
   dim3 grid((P.n_q + kBM - 1) / kBM, batch * P.heads);
-  attn_tc_kernel<BN, kTmemCols, kMinBlocks, kEmu><<<grid, kTcThreads, smem, st>>>(mq, mk, mv, mk2, mv2, P);
+  attn_tc_kernel<BN, kTmemCols, kMinBlocks, kEmu, kSplitP, kStages><<<grid, kTcThreads, smem, st>>>(mq, mk, mv, mk2, mv2, P);
   return check_cuda(cudaGetLastError(), "attn_tc_kernel launch");
 }
 
@@ -408,6 +446,19 @@ int launch_attn_tc(const void* q, const void* k, const void* v, void* o, int bat
     const char* e = getenv("VF_ATTN_EMU");
     emu = e ? atoi(e) : 0;
     if (emu < 0 || emu > 3) emu = 0;
+  }
+  static int split = -1;    // default: P in its own TMEM allocation, 3 CTAs / SM (see kernel comment); VF_ATTN_SPLITP=0: aliased P, 4 CTAs / SM
+  if (split < 0) {
+    const char* e = getenv("VF_ATTN_SPLITP");
+    split = e ? atoi(e) : 1;
+  }
+  if (P.d_pad <= 64 && split == 2) return launch_tc<64, 128, 3, 0, true, 3>(mq, mk, mv, mk2, mv2, P, batch, st);   // 3-stage K/V ring
+  if (P.d_pad <= 64 && split) {
+    switch (emu) {
+      case 1: return launch_tc<64, 128, 3, 1, true>(mq, mk, mv, mk2, mv2, P, batch, st);
+      case 2: return launch_tc<64, 128, 3, 2, true>(mq, mk, mv, mk2, mv2, P, batch, st);
+      default: return launch_tc<64, 128, 3, 0, true>(mq, mk, mv, mk2, mv2, P, batch, st);
+    }
   }
   if (P.d_pad <= 64) {                                                                   // 48 KB smem: 4 CTAs / SM
     switch (emu) {

@@ -294,6 +294,27 @@ fsai_fast_kernel(const fsaifast::Args A) {
   const long long stride = (long long)gridDim.x * C::RP;
   for (long long base = (long long)blockIdx.x * C::RP; base < A.n_pairs; base += stride) {
     fsaifast::phase_a<C>(A, base, threadIdx.x, sm_exch, sm_tw1);
+    if (A.prefetch && base + stride < A.n_pairs) {
+      // pull the next iteration's rows into L2 while this one is being transformed: 16 warps per SM
+      // cannot cover a DRAM round trip at the start of phase A, an L2 hit they can
+      using T = typename C::T;
+      constexpr int kLines = C::D * (int)sizeof(T) / 128;              // 128-byte lines per row
+      const long long row0 = (A.fused ? 1 : 2) * (base + stride);
+      const int n_rows = (A.fused ? 1 : 2) * C::RP;
+      const int n_ops = A.fused ? 3 : 2;
+      for (int i = threadIdx.x; i < n_ops * n_rows * kLines; i += C::kThreads) {
+        const int op = i / (n_rows * kLines);
+        const int rem = i - op * (n_rows * kLines);
+        const int r = rem / kLines, ln = rem - r * kLines;
+        const long long row = row0 + r;
+        if (row < A.rows) {
+          const T* p = op == 0 ? reinterpret_cast<const T*>(A.donor) + row * A.ld_donor
+                     : op == 1 ? reinterpret_cast<const T*>(A.dst_a) + row * A.ld_a
+                               : reinterpret_cast<const T*>(A.dst_b) + row * A.ld_b;
+          asm volatile("prefetch.global.L2 [%0];" :: "l"(p + ln * (128 / (int)sizeof(T))));
+        }
+      }
+    }
     __syncthreads();
     fsaifast::phase_b<C>(threadIdx.x, sm_exch, sm_rec);
     __syncthreads();
@@ -310,6 +331,11 @@ static int launch_fast(const FsaiParams& P, cudaStream_t st) {
   A.n_pairs = P.fused ? P.rows : (P.rows + 1) / 2;
   A.ld_donor = P.ld_donor; A.ld_a = P.ld_a; A.ld_out_a = P.ld_out_a; A.ld_b = P.ld_b; A.ld_out_b = P.ld_out_b;
   A.split = P.split;
+  {
+    static int pf = -1;
+    if (pf < 0) { const char* e = getenv("VF_FSAI_PREFETCH"); pf = e ? atoi(e) : 1; }
+    A.prefetch = pf;
+  }
   constexpr size_t smem = (size_t)C::kSmemFloats * sizeof(float);
   static int blocks_per_sm = 0;
   if (blocks_per_sm == 0) {
@@ -325,12 +351,22 @@ static int launch_fast(const FsaiParams& P, cudaStream_t st) {
   return check_cuda(cudaGetLastError(), "fsai_fast_kernel launch");
 }
 
+static bool small_cta() {      // tuning knob: VF_FSAI_SMALL=1 -> half the rows per CTA, five CTAs per SM
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("VF_FSAI_SMALL"); v = e ? atoi(e) : 0; }
+  return v != 0;
+}
+
 template <typename T>
 static int dispatch_fast(const FsaiParams& P, cudaStream_t st, bool* handled) {
   *handled = true;
   switch (P.d) {
-    case 320: return launch_fast<fsaifast::Cfg<T, 320, 4, 10, 8, 16>, 3>(P, st);
-    case 640: return launch_fast<fsaifast::Cfg<T, 640, 2, 20, 16, 8>, 3>(P, st);
+    case 320:
+      if (small_cta()) return launch_fast<fsaifast::Cfg<T, 320, 4, 10, 8, 8>, 5>(P, st);
+      return launch_fast<fsaifast::Cfg<T, 320, 4, 10, 8, 16>, 3>(P, st);
+    case 640:
+      if (small_cta()) return launch_fast<fsaifast::Cfg<T, 640, 2, 20, 16, 4>, 5>(P, st);
+      return launch_fast<fsaifast::Cfg<T, 640, 2, 20, 16, 8>, 3>(P, st);
     case 1280: return launch_fast<fsaifast::Cfg<T, 1280, 2, 20, 32, 8>, 1>(P, st);
     default: *handled = false; return 0;
   }

@@ -16,7 +16,7 @@
 //   phase C  (thread t again): conj twiddle, inverse L-point DFT, out = dst + y, vectorised store.
 //
 // Shared memory: one "unit" per (row, k1) = M*V complex + 16 B pad (stride 4*odd words), laid out
-// [lane pair][t][lane in pair][re, im], so phase A/C move 16 B per (k1, lane pair) with the quarter-warp
+// [lane pair][t][re pair, im pair], so phase A/C move 16 B per (k1, lane pair) with the quarter-warp
 // contiguous, and phase B's 16-B accesses of consecutive threads fall in distinct bank groups.
 // Per row and direction: D*8 B written + D*8 B read -- against 8 stages of that in the Stockham kernel.
 //
@@ -46,6 +46,7 @@ struct Args {
   long long ld_donor, ld_a, ld_out_a, ld_b, ld_out_b;
   int split;
   int fused;
+  int prefetch;        // L2-prefetch the next iteration's rows
 };
 
 template <typename T_, int D_, int V_, int L_, int M_, int RP_>
@@ -70,6 +71,9 @@ struct Cfg {
 // ---- V consecutive elements <-> floats ----------------------------------------------------------------
 template <typename T, int V> struct Vld;
 template <> struct Vld<float, 4> {
+  typedef float4 Raw;
+  static VF_HD Raw ld_raw(const float* p) { return *reinterpret_cast<const float4*>(p); }
+  static VF_HD void unpack(const Raw& u, float (&v)[4]) { v[0] = u.x; v[1] = u.y; v[2] = u.z; v[3] = u.w; }
   static VF_HD void ld(const float* p, float (&v)[4]) {
     const float4 u = *reinterpret_cast<const float4*>(p);
     v[0] = u.x; v[1] = u.y; v[2] = u.z; v[3] = u.w;
@@ -77,6 +81,9 @@ template <> struct Vld<float, 4> {
   static VF_HD void st(float* p, const float (&v)[4]) { *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]); }
 };
 template <> struct Vld<float, 2> {
+  typedef float2 Raw;
+  static VF_HD Raw ld_raw(const float* p) { return *reinterpret_cast<const float2*>(p); }
+  static VF_HD void unpack(const Raw& u, float (&v)[2]) { v[0] = u.x; v[1] = u.y; }
   static VF_HD void ld(const float* p, float (&v)[2]) {
     const float2 u = *reinterpret_cast<const float2*>(p);
     v[0] = u.x; v[1] = u.y;
@@ -94,6 +101,9 @@ VF_HD uint32_t bf_pack(float lo, float hi) {
   union { __nv_bfloat162 b; uint32_t i; } c; c.b = t; return c.i;
 }
 template <> struct Vld<__nv_bfloat16, 4> {
+  typedef uint2 Raw;
+  static VF_HD Raw ld_raw(const __nv_bfloat16* p) { return *reinterpret_cast<const uint2*>(p); }
+  static VF_HD void unpack(const Raw& u, float (&v)[4]) { v[0] = bf_lo(u.x); v[1] = bf_hi(u.x); v[2] = bf_lo(u.y); v[3] = bf_hi(u.y); }
   static VF_HD void ld(const __nv_bfloat16* p, float (&v)[4]) {
     const uint2 u = *reinterpret_cast<const uint2*>(p);
     v[0] = bf_lo(u.x); v[1] = bf_hi(u.x); v[2] = bf_lo(u.y); v[3] = bf_hi(u.y);
@@ -103,6 +113,9 @@ template <> struct Vld<__nv_bfloat16, 4> {
   }
 };
 template <> struct Vld<__nv_bfloat16, 2> {
+  typedef uint32_t Raw;
+  static VF_HD Raw ld_raw(const __nv_bfloat16* p) { return *reinterpret_cast<const uint32_t*>(p); }
+  static VF_HD void unpack(const Raw& u, float (&v)[2]) { v[0] = bf_lo(u); v[1] = bf_hi(u); }
   static VF_HD void ld(const __nv_bfloat16* p, float (&v)[2]) {
     const uint32_t u = *reinterpret_cast<const uint32_t*>(p);
     v[0] = bf_lo(u); v[1] = bf_hi(u);
@@ -143,12 +156,13 @@ template <int V> VF_HD void load4(const float* p, float (&q)[4]) {
 }
 VF_HD void store4(float* p, float a, float b, float c, float d) { *reinterpret_cast<float4*>(p) = make_float4(a, b, c, d); }
 
-// unit layout: [lane pair][t][lane in pair][re, im]
+// unit layout: [lane pair][t][re of the pair, im of the pair]: a 16-byte access is exactly the two
+// 64-bit register pairs the packed arithmetic works on (no register shuffling on either side)
 template <typename C>
 VF_HD void unit_store(float* unit, int t, const CVec<C::V>& x) {
 #pragma unroll
   for (int ep = 0; ep < C::V / 2; ++ep)
-    store4(unit + ep * (C::M * 4) + t * 4, x.re.p[ep].x, x.im.p[ep].x, x.re.p[ep].y, x.im.p[ep].y);
+    store4(unit + ep * (C::M * 4) + t * 4, x.re.p[ep].x, x.re.p[ep].y, x.im.p[ep].x, x.im.p[ep].y);
 }
 template <typename C>
 VF_HD void unit_load(const float* unit, int t, CVec<C::V>& x) {
@@ -156,8 +170,8 @@ VF_HD void unit_load(const float* unit, int t, CVec<C::V>& x) {
   for (int ep = 0; ep < C::V / 2; ++ep) {
     float q[4];
     load4<C::V>(unit + ep * (C::M * 4) + t * 4, q);
-    x.re.p[ep] = make_float2(q[0], q[2]);
-    x.im.p[ep] = make_float2(q[1], q[3]);
+    x.re.p[ep] = make_float2(q[0], q[1]);
+    x.im.p[ep] = make_float2(q[2], q[3]);
   }
 }
 
@@ -297,16 +311,6 @@ VF_HD void phase_c(const Args& A, long long pair_base, int tid, const float* sm_
   const int row = tid / M, t = tid - row * M;
   const long long pair = pair_base + row;
   if (pair >= A.n_pairs) return;
-  CVec<V> x[L];
-#pragma unroll
-  for (int k1 = 0; k1 < L; ++k1) {
-    unit_load<C>(sm_exch + (row * L + k1) * C::kUnitFloats, t, x[k1]);
-    if (k1 > 0) {
-      const float2 w = *reinterpret_cast<const float2*>(sm_tw1 + 2 * (k1 * M + t));
-      x[k1] = fftreg::cmul(x[k1], w.x, -w.y);
-    }
-  }
-  fftreg::dft_inplace<L, true>(x);
   const T* pa; T* oa; const T* pb; T* ob;
   bool has_b = true;
   if (A.fused) {
@@ -322,12 +326,31 @@ VF_HD void phase_c(const Args& A, long long pair_base, int tid, const float* sm_
     pb = reinterpret_cast<const T*>(A.dst_a) + (has_b ? r1 : r0) * A.ld_a;
     ob = reinterpret_cast<T*>(A.out_a) + (has_b ? r1 : r0) * A.ld_out_a;
   }
+  // dst is read again (an L2 hit: phase A touched it a few microseconds ago) instead of being carried in
+  // registers through phase B; issue those loads FIRST so that their latency hides behind the inverse DFT.
+  typename Vld<T, V>::Raw ra[L], rb[L];
+#pragma unroll
+  for (int r = 0; r < L; ++r) {
+    const int col = V * (t + M * r);
+    ra[r] = Vld<T, V>::ld_raw(pa + col);
+    rb[r] = Vld<T, V>::ld_raw(pb + col);
+  }
+  CVec<V> x[L];
+#pragma unroll
+  for (int k1 = 0; k1 < L; ++k1) {
+    unit_load<C>(sm_exch + (row * L + k1) * C::kUnitFloats, t, x[k1]);
+    if (k1 > 0) {
+      const float2 w = *reinterpret_cast<const float2*>(sm_tw1 + 2 * (k1 * M + t));
+      x[k1] = fftreg::cmul(x[k1], w.x, -w.y);
+    }
+  }
+  fftreg::dft_inplace<L, true>(x);
 #pragma unroll
   for (int r = 0; r < L; ++r) {
     const int col = V * (t + M * r);
     float a[V], b[V];
-    Vld<T, V>::ld(pa + col, a);
-    if (has_b) Vld<T, V>::ld(pb + col, b);
+    Vld<T, V>::unpack(ra[r], a);
+    Vld<T, V>::unpack(rb[r], b);
 #pragma unroll
     for (int e = 0; e < V; ++e) a[e] += x[r].re.get(e);
     Vld<T, V>::st(oa + col, a);
