@@ -316,7 +316,7 @@ def main():
                 traffic = json.load(open(tp)).get("dram_bytes_per_launch")
             except Exception:
                 traffic = None
-        roof = dict(bound="tensor", kernel="vf::attn_tc_kernel<BN=64, 128 TMEM cols, 4 CTAs/SM> (N=4096, 8 heads x d40)", achieved=ach,
+        roof = dict(bound="tensor", kernel="vf::attn_tc_kernel<BN=64, S/O 128 + P 32 TMEM cols, 3 CTAs/SM> (N=4096, 8 heads x d40)", achieved=ach,
                     peak=pk["tc_sustained"], unit="TFLOP/s", frac=ach / pk["tc_sustained"], traffic=traffic,
                     peak_source=f"{pk['src']} sustained bf16 (kernel timed inside a long step); burst {pk['tc_burst']}",
                     frac_of_burst=ach / pk["tc_burst"], launches_timed=len(attn_ms), avg_launch_ms=avg_ms,

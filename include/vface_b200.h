@@ -28,7 +28,7 @@ extern "C" {
 #define VF_F32 0
 #define VF_BF16 1
 
-#define VF_ABI_VERSION 2
+#define VF_ABI_VERSION 3
 
 /* ABI version of the loaded library (== VF_ABI_VERSION). */
 int vf_abi_version(void);
@@ -142,6 +142,16 @@ long long vf_group_norm_workspace_floats(int n, int hw, int groups);
 int vf_group_norm_nhwc(const void* x, const void* add_nc, const void* gamma, const void* beta, void* y,
                        float* workspace, int n, int hw, int c, int groups, float eps, int silu,
                        int dtype, void* stream);
+
+/*
+ * The same over the channel concatenation [x (c1 channels) ; x2 (c2 channels)] of two channels-last tensors,
+ * read in place: y (n, hw, c1+c2) = act(GN(cat(x, x2) + add_nc)).  Replaces `th.cat([h, hs.pop()], dim=1)`
+ * (openaimodel.py:899) followed by the first GroupNorm of the output-block ResBlock (:201-205): the
+ * concatenated skip tensor is never materialised.  x2 == NULL reduces to vf_group_norm_nhwc.
+ */
+int vf_group_norm_nhwc_cat(const void* x, int c1, const void* x2, int c2, const void* add_nc,
+                           const void* gamma, const void* beta, void* y, float* workspace,
+                           int n, int hw, int groups, float eps, int silu, int dtype, void* stream);
 
 /*
  * res = x + y + bias ; out = LayerNorm(res) * gamma + beta over the last axis (c).

@@ -196,11 +196,33 @@ def golden_unet_full():
     save("unet_full.npz", out=y.numpy(), x_recon_lat=x[2, :4].numpy())
 
 
+VAE_SMALL = dict(double_z=True, z_channels=4, resolution=64, in_channels=3, out_ch=3, ch=32, ch_mult=[1, 2, 4, 4],
+                 num_res_blocks=2, attn_resolutions=[], dropout=0.0)
+
+
+def golden_vae_decoder():
+    """Reference first-stage Decoder (model.py:462-570) + post_quant_conv (autoencoder.py:330-333) on a
+    reduced ddconfig (ch 32: mid attention width 128), weights from vface_b200.synth (seed 3)."""
+    from ldm.modules.diffusionmodules.model import Decoder
+    from vface_b200 import synth
+    with quiet():
+        dec = Decoder(**VAE_SMALL).eval()
+    pq = torch.nn.Conv2d(4, 4, 1)
+    sd = synth.synth_state_dict({**{"decoder." + k: v for k, v in dec.state_dict().items()},
+                                 **{"post_quant_conv." + k: v for k, v in pq.state_dict().items()}}, seed=3)
+    dec.load_state_dict({k[len("decoder."):]: v for k, v in sd.items() if k.startswith("decoder.")})
+    pq.load_state_dict({k[len("post_quant_conv."):]: v for k, v in sd.items() if k.startswith("post_quant_conv.")})
+    z = torch.randn(2, 4, 8, 8, generator=torch.Generator().manual_seed(21))
+    with torch.no_grad():
+        y = dec(pq(z / 0.18215))
+    save("vae_decoder.npz", z=z.numpy(), out=y.numpy(), keys=np.array(sorted(sd.keys())))
+
+
 def main():
     if not rh.available():
         sys.exit("reference not mounted; golden vectors can only be generated in the build container")
     rh.install()
-    which = sys.argv[1:] or ["fsai", "warp", "attn_hooks", "schedule", "sampler_small", "unet_full"]
+    which = sys.argv[1:] or ["fsai", "warp", "attn_hooks", "schedule", "sampler_small", "unet_full", "vae_decoder"]
     for w in which:
         globals()["golden_" + w]()
 

@@ -186,3 +186,18 @@ def test_halo_exchange_gloo(world, frames):
     ret = mgr.dict()
     mp.spawn(_halo_worker, args=(world, port, frames, ret), nprocs=world, join=True)
     assert all(ret.get(r) for r in range(world))
+
+
+def test_vae_decoder_state_dict_keys_match_reference_golden():
+    """The first-stage decoder mirror has exactly the reference's parameter names (so `first_stage_model.*`
+    of the reference checkpoint loads as is); names recorded from the reference in tests/golden/vae_decoder.npz."""
+    import os
+    import numpy as np
+    from vface_b200.ldm.modules.diffusionmodules.model import AutoencoderKLDecoder
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "vae_decoder.npz"))
+    small = dict(double_z=True, z_channels=4, resolution=64, in_channels=3, out_ch=3, ch=32, ch_mult=[1, 2, 4, 4],
+                 num_res_blocks=2, attn_resolutions=[], dropout=0.0)
+    assert sorted(AutoencoderKLDecoder(small).state_dict().keys()) == [str(k) for k in gold["keys"]]
+    full = AutoencoderKLDecoder().state_dict()
+    assert full["decoder.conv_in.weight"].shape == (512, 4, 3, 3) and full["decoder.mid.attn_1.q.weight"].shape == (512, 512, 1, 1)
+    assert full["decoder.conv_out.weight"].shape == (3, 128, 3, 3) and len(full) == 140

@@ -65,7 +65,12 @@ def test_sampler_small_vs_reference_golden(kind, dtype, tol):
         err = rel_l2(inter["x_inter"][1 + i], want[i])
         assert err < tol, (i, err)
     assert rel_l2(samples, gold[f"samples_{kind}"]) < tol
-    assert rel_l2(torch.stack(inter["pred_x0"][1:]), gold[f"pred_x0_{kind}"]) < tol
+    # pred_x0 = (x - sqrt(1-a_t) eps) / sqrt(a_t) is not a per-step latent: at the first steps (t = 901:
+    # sqrt(a_t) = 0.08) it divides the eps error by sqrt(a_t), so in bf16 it is held to 2x the latent bound
+    # over the whole trajectory and to the latent bound itself over the second half (a_t >= 0.27).
+    px0, want0 = torch.stack(inter["pred_x0"][1:]), gold[f"pred_x0_{kind}"]
+    assert rel_l2(px0, want0) < (tol if dtype == torch.float32 else 2 * tol)
+    assert rel_l2(px0[S // 2:], want0[S // 2:]) < tol
 
 
 def test_inversion_dir_and_dict_agree(tmp_path):

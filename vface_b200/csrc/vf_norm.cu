@@ -45,6 +45,8 @@ constexpr int kGnMaxGroups = 32;
 
 struct GnParams {
   const void* x; const void* add_nc; const void* gamma; const void* beta; void* y;
+  const void* x2;       // second source (channels [c1, c)) of a channel-concatenated input, or null
+  int c1;               // channels taken from x (== c when x2 is null)
   float* ws;            // [n][slabs][groups][2] partial (sum, sumsq)
   int n, hw, c, groups, slabs, rows_per_slab;
   float eps;
@@ -78,7 +80,9 @@ gn_stats_kernel(const GnParams P) {
   const int cpg = P.c / P.groups;
   const int r0 = slab * P.rows_per_slab;
   const int r1 = min(P.hw, r0 + P.rows_per_slab);
-  const T* x = reinterpret_cast<const T*>(P.x) + (size_t)n * P.hw * P.c;
+  const int c2 = P.c - P.c1;
+  const T* x = reinterpret_cast<const T*>(P.x) + (size_t)n * P.hw * P.c1;
+  const T* x2 = P.x2 ? reinterpret_cast<const T*>(P.x2) + (size_t)n * P.hw * c2 : nullptr;
   const T* add = P.add_nc ? reinterpret_cast<const T*>(P.add_nc) + (size_t)n * P.c : nullptr;
   if (M.active) {
     float sum[CPT][E], sq[CPT][E], av[CPT][E];
@@ -95,7 +99,7 @@ gn_stats_kernel(const GnParams P) {
         const int ch = (M.my_chunk + k * kGnThreads) * E;
         if (ch < P.c) {
           float v[E];
-          V16<T>::ld(x + (size_t)r * P.c + ch, v);
+          V16<T>::ld(ch < P.c1 ? x + (size_t)r * P.c1 + ch : x2 + (size_t)r * c2 + (ch - P.c1), v);
 #pragma unroll
           for (int j = 0; j < E; ++j) { const float t = v[j] + av[k][j]; sum[k][j] += t; sq[k][j] = fmaf(t, t, sq[k][j]); }
         }
@@ -153,7 +157,9 @@ gn_apply_kernel(const GnParams P) {
   if (!M.active) return;
   const int r0 = slab * P.rows_per_slab;
   const int r1 = min(P.hw, r0 + P.rows_per_slab);
-  const T* x = reinterpret_cast<const T*>(P.x) + (size_t)n * P.hw * P.c;
+  const int c2 = P.c - P.c1;
+  const T* x = reinterpret_cast<const T*>(P.x) + (size_t)n * P.hw * P.c1;
+  const T* x2 = P.x2 ? reinterpret_cast<const T*>(P.x2) + (size_t)n * P.hw * c2 : nullptr;
   T* y = reinterpret_cast<T*>(P.y) + (size_t)n * P.hw * P.c;
   const T* add = P.add_nc ? reinterpret_cast<const T*>(P.add_nc) + (size_t)n * P.c : nullptr;
   const T* gamma = reinterpret_cast<const T*>(P.gamma);
@@ -183,7 +189,7 @@ gn_apply_kernel(const GnParams P) {
       const int ch = (M.my_chunk + k * kGnThreads) * E;
       if (ch < P.c) {
         float v[E];
-        V16<T>::ld(x + (size_t)r * P.c + ch, v);
+        V16<T>::ld(ch < P.c1 ? x + (size_t)r * P.c1 + ch : x2 + (size_t)r * c2 + (ch - P.c1), v);
 #pragma unroll
         for (int j = 0; j < E; ++j) {
           float t = fmaf(v[j], scale[k][j], shift[k][j]);
@@ -364,9 +370,18 @@ extern "C" long long vf_group_norm_workspace_floats(int n, int hw, int groups) {
 extern "C" int vf_group_norm_nhwc(const void* x, const void* add_nc, const void* gamma, const void* beta, void* y,
                                   float* workspace, int n, int hw, int c, int groups, float eps, int silu,
                                   int dtype, void* stream) {
+  return vf_group_norm_nhwc_cat(x, c, nullptr, 0, add_nc, gamma, beta, y, workspace, n, hw, groups, eps, silu, dtype, stream);
+}
+
+extern "C" int vf_group_norm_nhwc_cat(const void* x, int c1, const void* x2, int c2, const void* add_nc,
+                                      const void* gamma, const void* beta, void* y, float* workspace,
+                                      int n, int hw, int groups, float eps, int silu, int dtype, void* stream) {
   using namespace vf;
   if (int rc = check_device()) return rc;
+  const int c = c1 + (x2 ? c2 : 0);
   if (!x || !gamma || !beta || !y || !workspace) return fail("vf_group_norm_nhwc: null pointer");
+  if (x2 && (c2 <= 0 || c1 % (dtype == VF_F32 ? 4 : 8) || c2 % (dtype == VF_F32 ? 4 : 8) || !al16(x2)))
+    return fail("vf_group_norm_nhwc_cat: both channel counts must be multiples of a 16-byte vector (c1=%d c2=%d)", c1, c2);
   if (dtype != VF_F32 && dtype != VF_BF16) return fail("vf_group_norm_nhwc: bad dtype %d", dtype);
   const int e = dtype == VF_F32 ? 4 : 8;
   if (n <= 0 || hw <= 0 || c <= 0 || groups <= 0 || groups > kGnMaxGroups || c % groups || c % e)
@@ -377,6 +392,7 @@ extern "C" int vf_group_norm_nhwc(const void* x, const void* add_nc, const void*
     return fail("vf_group_norm_nhwc: pointers must be 16-byte aligned");
   GnParams P;
   P.x = x; P.add_nc = add_nc; P.gamma = gamma; P.beta = beta; P.y = y; P.ws = workspace;
+  P.x2 = x2; P.c1 = x2 ? c1 : c;
   P.n = n; P.hw = hw; P.c = c; P.groups = groups; P.eps = eps; P.silu = silu;
   gn_plan(n, hw, &P.slabs, &P.rows_per_slab);
   dim3 grid(P.slabs, n);

@@ -37,7 +37,8 @@ class DiffusionWrapper(nn.Module):
 
 
 class LatentDiffusion(nn.Module):
-    def __init__(self, unet_config=None, timesteps=1000, linear_start=0.00085, linear_end=0.012, unet=None):
+    def __init__(self, unet_config=None, timesteps=1000, linear_start=0.00085, linear_end=0.012, unet=None,
+                 first_stage_config=None):
         super().__init__()
         cfg = dict(REFACE_UNET_CONFIG)
         if unet_config:
@@ -46,6 +47,10 @@ class LatentDiffusion(nn.Module):
         self.num_timesteps = timesteps
         self.parameterization = "eps"
         self.scale_factor = 0.18215
+        # the step after the path: only built on request, `{}` = the REFace ddconfig
+        if first_stage_config is not None:
+            from .ldm.modules.diffusionmodules.model import AutoencoderKLDecoder
+            self.first_stage_model = AutoencoderKLDecoder(first_stage_config or None)
         betas = make_beta_schedule("linear", timesteps, linear_start=linear_start, linear_end=linear_end)
         alphas_cumprod = np.cumprod(1.0 - betas, axis=0)
         alphas_cumprod_prev = np.append(1.0, alphas_cumprod[:-1])
@@ -70,6 +75,13 @@ class LatentDiffusion(nn.Module):
         a = self.alphas_cumprod[t].sqrt().view(-1, 1, 1, 1)
         s = (1.0 - self.alphas_cumprod[t]).sqrt().view(-1, 1, 1, 1)
         return a * x_start + s * noise
+
+    def decode_first_stage(self, z):
+        """ddpm.py:1277-1284 (plain path) -> AutoencoderKL.decode: x = decoder(post_quant_conv(z / scale_factor))."""
+        if not hasattr(self, "first_stage_model"):
+            raise RuntimeError("LatentDiffusion was built without first_stage_config")
+        p = next(self.first_stage_model.parameters())
+        return self.first_stage_model.decode((1.0 / self.scale_factor * z).to(p.dtype))
 
     def to_compute_dtype(self, dtype):
         """Cast the UNet parameters (bf16 on the throughput path); schedule buffers stay fp32."""

@@ -31,6 +31,8 @@ class TimestepBlock(nn.Module):
 
 class TimestepEmbedSequential(nn.Sequential, TimestepBlock):
     def forward(self, x, emb, context=None):
+        """x may be a (h, skip) pair: the decoder's channel concatenation, consumed in place by the
+        leading ResBlock (every output block starts with one)."""
         for layer in self:
             if isinstance(layer, TimestepBlock):
                 x = layer(x, emb)
@@ -108,18 +110,33 @@ class ResBlock(TimestepBlock):
         """GN-SiLU-conv, + emb, GN-SiLU-conv, + skip (reference :255-275) on channels-last activations:
         the two GroupNorm+SiLU are one fused kernel each, the `+ emb_out` and the first conv bias ride
         inside the second GroupNorm, and the second conv bias rides inside the residual add."""
+        x2t = None
+        if isinstance(x, tuple):
+            # decoder skip concatenation th.cat([h, hs.pop()], dim=1) (reference :899), never materialised:
+            # the first GroupNorm reads both sources, the 1x1 skip convolution becomes two accumulating GEMMs
+            x, x2 = x
+            x2t = x2.permute(0, 2, 3, 1).contiguous()
         n, c, hh, ww = x.shape
         xt = x.permute(0, 2, 3, 1).contiguous()                  # NHWC; a view for channels_last input
         gn1, conv1 = self.in_layers[0], self.in_layers[2]
         gn2, conv2 = self.out_layers[0], self.out_layers[3]
-        g1 = ops.group_norm_nhwc(xt, gn1.weight, gn1.bias, gn1.eps, gn1.num_groups, silu=True)
+        g1 = ops.group_norm_nhwc(xt, gn1.weight, gn1.bias, gn1.eps, gn1.num_groups, silu=True, x2=x2t)
         h1 = F.conv2d(g1.permute(0, 3, 1, 2), conv1.weight, None, padding=1)
         add = self.emb_layers(emb).type(h1.dtype) + conv1.bias
         g2 = ops.group_norm_nhwc(h1.permute(0, 2, 3, 1).contiguous(), gn2.weight, gn2.bias, gn2.eps, gn2.num_groups,
                                  silu=True, add_nc=add)
         h2 = F.conv2d(g2.permute(0, 3, 1, 2), conv2.weight, None, padding=1).permute(0, 2, 3, 1).contiguous()
         bias = conv2.bias
-        if isinstance(self.skip_connection, nn.Identity):
+        if x2t is not None:
+            if isinstance(self.skip_connection, nn.Identity) or self.skip_connection.kernel_size != (1, 1):
+                raise NotImplementedError("a concatenated ResBlock input needs the 1x1 skip convolution")
+            w = self.skip_connection.weight.reshape(self.out_channels, self.channels)
+            rows = n * hh * ww
+            skip = torch.mm(xt.reshape(rows, c), w[:, :c].t())
+            skip.addmm_(x2t.reshape(rows, self.channels - c), w[:, c:].t())
+            skip = skip.reshape(n, hh, ww, self.out_channels)
+            bias = bias + self.skip_connection.bias
+        elif isinstance(self.skip_connection, nn.Identity):
             skip = xt
         elif self.skip_connection.kernel_size == (1, 1):
             skip = F.linear(xt, self.skip_connection.weight.reshape(self.out_channels, c))
@@ -256,8 +273,7 @@ class UNetModel(nn.Module):
         h = self.middle_block(h, emb, context)
         features = []
         for module in self.output_blocks:
-            h = torch.cat([h, hs.pop()], dim=1)
-            h = module(h, emb, context)
+            h = module((h, hs.pop()), emb, context)
             if return_features:
                 features.append(h)
         gn = self.out[0]

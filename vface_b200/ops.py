@@ -257,23 +257,35 @@ def _rows_c(t: torch.Tensor, name: str):
 
 
 def group_norm_nhwc(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, eps: float, groups: int = 32,
-                    silu: bool = False, add_nc: Optional[torch.Tensor] = None) -> torch.Tensor:
+                    silu: bool = False, add_nc: Optional[torch.Tensor] = None,
+                    x2: Optional[torch.Tensor] = None) -> torch.Tensor:
     """GroupNorm (+SiLU) of channels-last activations x: (n, ..., c); add_nc: optional (n, c) vector
-    added to every position before the statistics (ResBlock `h + emb_out`)."""
-    _need_cuda(x, weight, bias, add_nc)
+    added to every position before the statistics (ResBlock `h + emb_out`).
+    x2: optional second channels-last tensor (n, ..., c2): the norm runs over the channel concatenation
+    [x ; x2] read in place (the skip-connection `th.cat` of the UNet decoder, openaimodel.py:899) and
+    returns the normalised (n, ..., c + c2) tensor."""
+    _need_cuda(x, weight, bias, add_nc, x2)
     if not x.is_contiguous() or x.dim() < 3:
         raise ValueError("group_norm_nhwc: x must be a contiguous (n, ..., c) tensor")
-    n, c = x.shape[0], x.shape[-1]
-    hw = x.numel() // (n * c)
-    if weight.dtype != x.dtype or bias.dtype != x.dtype or (add_nc is not None and (add_nc.dtype != x.dtype or tuple(add_nc.shape) != (n, c))):
+    n, c1 = x.shape[0], x.shape[-1]
+    hw = x.numel() // (n * c1)
+    c2 = 0
+    if x2 is not None:
+        if not x2.is_contiguous() or x2.shape[:-1] != x.shape[:-1] or x2.dtype != x.dtype:
+            raise ValueError("group_norm_nhwc: x2 must be contiguous and match x in all but the channel axis")
+        c2 = x2.shape[-1]
+    c = c1 + c2
+    if weight.dtype != x.dtype or bias.dtype != x.dtype or weight.numel() != c or bias.numel() != c or \
+            (add_nc is not None and (add_nc.dtype != x.dtype or tuple(add_nc.shape) != (n, c))):
         raise ValueError("group_norm_nhwc: parameter dtype/shape mismatch")
     lib = _lib.load()
     ws = torch.empty(lib.vf_group_norm_workspace_floats(n, hw, groups), dtype=torch.float32, device=x.device)
-    y = torch.empty_like(x)
-    rc = lib.vf_group_norm_nhwc(x.data_ptr(), add_nc.contiguous().data_ptr() if add_nc is not None else None,
-                                weight.data_ptr(), bias.data_ptr(), y.data_ptr(), ws.data_ptr(), n, hw, c, groups,
-                                float(eps), int(silu), _code(x), _stream(x))
-    _lib.check(rc, "vf_group_norm_nhwc")
+    y = torch.empty(x.shape[:-1] + (c,), dtype=x.dtype, device=x.device)
+    rc = lib.vf_group_norm_nhwc_cat(x.data_ptr(), c1, x2.data_ptr() if x2 is not None else None, c2,
+                                    add_nc.contiguous().data_ptr() if add_nc is not None else None,
+                                    weight.data_ptr(), bias.data_ptr(), y.data_ptr(), ws.data_ptr(), n, hw, groups,
+                                    float(eps), int(silu), _code(x), _stream(x))
+    _lib.check(rc, "vf_group_norm_nhwc_cat")
     _count(2)
     return y
 
