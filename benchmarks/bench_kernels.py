@@ -1,6 +1,6 @@
 """Kernel microbenchmarks: BASELINE.json configs 3 (attention) and 4 (FSAI, flow warp) + CFG/DDIM.
 
-    python benchmarks/bench_kernels.py [--only attn|fsai|warp|ddim] [--iters 20] [--json out.json]
+    python benchmarks/bench_kernels.py [--only attn|fsai|warp|ddim|glue] [--iters 20] [--json out.json]
 
 Timing: CUDA events on the launching (current) stream, >= 3 warm-up launches, an L2 flush (write of a
 256 MiB buffer) before every timed launch.  Rooflines use /root/repo/MEASURED_PEAKS.json when present,
@@ -135,6 +135,36 @@ def bench_ddim(res, iters):
         print(f"{name:62s} {med:8.3f} ms  {gbs:8.1f} GB/s  {100 * gbs / pk['hbm']:5.1f}% of {pk['src']} HBM")
 
 
+def bench_glue(res, iters):
+    """The fused glue kernels of the UNet at the shapes of one 32-frame step (UNet batch 96)."""
+    pk = peaks()
+    dt, e = torch.bfloat16, 2
+    g = torch.Generator(device="cuda").manual_seed(0)
+    rn = lambda *s: torch.randn(*s, device="cuda", generator=g).to(dt)
+
+    def rec(name, fn, by):
+        med, best = time_kernel(fn, iters)
+        gbs = by / (med * 1e-3) / 1e9
+        res.append(dict(kernel=name, ms=med, ms_best=best, gbs=gbs, frac=gbs / pk["hbm"], bound="hbm", peaks=pk["src"]))
+        print(f"{name:62s} {med:8.3f} ms  {gbs:8.1f} GB/s  {100 * gbs / pk['hbm']:5.1f}% of {pk['src']} HBM")
+
+    for n, c in ((4096, 320), (1024, 640), (256, 1280)):
+        b = 96
+        h = rn(b, n, 8 * c)
+        rec(f"geglu rows={b * n} k={4 * c}", lambda: ops.geglu(h), 3.0 * b * n * 4 * c * e)
+        x = rn(b, n, c)
+        w, bb = rn(c), rn(c)
+        rec(f"group_norm+silu NHWC n={b} hw={n} c={c} (2 reads + 1 write)", lambda: ops.group_norm_nhwc(x, w, bb, 1e-5, 32, silu=True),
+            3.0 * b * n * c * e)
+        y = rn(b, n, c)
+        rec(f"add_bias rows={b * n} c={c}", lambda: ops.add_bias(x, y, bb), 3.0 * b * n * c * e)
+        rec(f"add+layer_norm rows={b * n} c={c} (2 reads + 2 writes)", lambda: ops.add_layer_norm(x, w, bb, 1e-5, y=y), 4.0 * b * n * c * e)
+    x1, x2 = rn(96, 4096, 320), rn(96, 4096, 320)
+    w, bb = rn(640), rn(640)
+    rec("group_norm+silu over cat(320+320) n=96 hw=4096", lambda: ops.group_norm_nhwc(x1, w, bb, 1e-5, 32, silu=True, x2=x2),
+        3.0 * 96 * 4096 * 640 * e)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default="")
@@ -143,7 +173,7 @@ def main():
     a = ap.parse_args()
     res = []
     print(torch.cuda.get_device_name(0), "| peaks:", peaks())
-    for name, fn in (("attn", bench_attn), ("fsai", bench_fsai), ("warp", bench_warp), ("ddim", bench_ddim)):
+    for name, fn in (("attn", bench_attn), ("fsai", bench_fsai), ("warp", bench_warp), ("ddim", bench_ddim), ("glue", bench_glue)):
         if a.only and a.only != name:
             continue
         fn(res, a.iters)

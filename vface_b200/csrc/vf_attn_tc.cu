@@ -233,6 +233,13 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
       uint32_t sr[BN / 32][32];
 #pragma unroll
       for (int c = 0; c < BN / 32; ++c) tmem_ld_x32(tm_s + lane_off + c * 32, sr[c]);
+      if (kSplitP && j > 0) {
+        // P_{j-1} hand-over, deferred to here so that its TMEM-store latency overlaps this tile's S load
+        tmem_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars.p_full);
+      }
       tmem_wait_ld();
       if (kSplitP) {
         tc_fence_before();
@@ -323,10 +330,12 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
           tmem_st_x8(tm_o + lane_off + c, o8);
         }
       }
-      tmem_wait_st();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&bars.p_full);
+      if (!kSplitP || j + 1 == n_tiles) {
+        tmem_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars.p_full);
+      }
     }
 
     // ---- epilogue: O / l -> bf16 -> global ------------------------------------------------------

@@ -11,6 +11,10 @@
 // statistics in fp32.  GroupNorm is two passes (statistics, apply): 2 reads + 1 write of x, against
 // 5 passes + 2 layout conversions for the eager GroupNorm(NCHW)/SiLU/add chain it replaces.
 #include "vf_common.cuh"
+#include "vf_sm100.cuh"
+
+#include <cooperative_groups.h>
+#include <cstdlib>
 
 namespace vf {
 
@@ -212,6 +216,231 @@ static void gn_plan(int n, int hw, int* slabs, int* rows_per_slab) {
   *slabs = (hw + rps - 1) / rps;
 }
 
+// ---- one-pass GroupNorm: a thread-block cluster per sample, the sample resident in shared memory ------------
+// The two-pass form reads x twice (statistics, apply): 3 HBM passes.  Here a cluster of 1..16 CTAs owns one
+// sample: each CTA pulls its contiguous slab of rows into shared memory with 1-D bulk TMA copies (chunked, so
+// the statistics run under the loads), the per-group partials of the CTAs meet through distributed shared
+// memory in a fixed order (bit-reproducible), and the apply pass reads the slab from shared memory: 1 read +
+// 1 write of HBM and one launch.  Used whenever hw*c*e / 16 fits a CTA's shared memory; the widest
+// concatenated decoder inputs at 64x64 (5-8 MB per sample) stay on the two-pass kernels.
+constexpr int kGnChunks = 8;
+
+struct GnClusterSmem {
+  uint64_t bar[kGnChunks];
+  float red[2 * kGnMaxGroups];     // this CTA's per-group (sum, sumsq), read by the whole cluster
+  float mean[kGnMaxGroups], rstd[kGnMaxGroups];
+};
+
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               :: "r"(sm100::smem_u32(dst)), "l"(src), "r"(bytes), "r"(sm100::smem_u32(bar)) : "memory");
+}
+
+template <typename T, int CPT>
+__global__ void __launch_bounds__(kGnThreads, 1)
+gn_cluster_kernel(const GnParams P) {
+  namespace cg = cooperative_groups;
+  constexpr int E = V16<T>::E;
+  extern __shared__ __align__(128) unsigned char gn_smem[];
+  cg::cluster_group cluster = cg::this_cluster();
+  const int cs = (int)cluster.num_blocks();
+  const int rank = (int)cluster.block_rank();
+  const int n = blockIdx.x / cs;
+  const int rows_per_cta = P.rows_per_slab;                 // ceil(hw / cs), set by the host
+  const int r0 = min(P.hw, rank * rows_per_cta);
+  const int nrows = min(P.hw, r0 + rows_per_cta) - r0;
+  const int c1 = P.c1, c2 = P.c - P.c1;
+  const GnMap M(P.c, E);
+  // shared memory: header | slab 1 (rows x c1) | slab 2 (rows x c2) | per-(row lane, channel) partials
+  GnClusterSmem* H = reinterpret_cast<GnClusterSmem*>(gn_smem);
+  T* slab1 = reinterpret_cast<T*>(gn_smem + 1024);
+  T* slab2 = slab1 + (size_t)rows_per_cta * c1;
+  float* s_psum = reinterpret_cast<float*>(slab2 + (size_t)rows_per_cta * c2);
+  float* s_psq = s_psum + M.rpb * P.c;
+
+  const int rows_per_chunk = (nrows + kGnChunks - 1) / kGnChunks;
+  if (threadIdx.x == 0) {
+    for (int k = 0; k < kGnChunks; ++k) sm100::mbar_init(&H->bar[k], 1);
+    sm100::fence_barrier_init();
+    const T* g1 = reinterpret_cast<const T*>(P.x) + ((size_t)n * P.hw + r0) * c1;
+    const T* g2 = P.x2 ? reinterpret_cast<const T*>(P.x2) + ((size_t)n * P.hw + r0) * c2 : nullptr;
+    for (int k = 0; k < kGnChunks; ++k) {
+      const int a = min(nrows, k * rows_per_chunk), b = min(nrows, (k + 1) * rows_per_chunk);
+      const uint32_t b1 = (uint32_t)((size_t)(b - a) * c1 * sizeof(T));
+      const uint32_t b2 = g2 ? (uint32_t)((size_t)(b - a) * c2 * sizeof(T)) : 0u;
+      sm100::mbar_arrive_expect_tx(&H->bar[k], b1 + b2);      // 0 bytes: completes at once
+      if (b1) bulk_g2s(slab1 + (size_t)a * c1, g1 + (size_t)a * c1, b1, &H->bar[k]);
+      if (b2) bulk_g2s(slab2 + (size_t)a * c2, g2 + (size_t)a * c2, b2, &H->bar[k]);
+    }
+  }
+  __syncthreads();
+
+  const int cpg = P.c / P.groups;
+  const T* add = P.add_nc ? reinterpret_cast<const T*>(P.add_nc) + (size_t)n * P.c : nullptr;
+  if (M.active) {
+    float sum[CPT][E], sq[CPT][E], av[CPT][E];
+#pragma unroll
+    for (int k = 0; k < CPT; ++k) {
+      const int ch = (M.my_chunk + k * kGnThreads) * E;
+#pragma unroll
+      for (int j = 0; j < E; ++j) { sum[k][j] = 0.f; sq[k][j] = 0.f; av[k][j] = 0.f; }
+      if (add && ch < P.c) V16<T>::ld(add + ch, av[k]);
+    }
+    for (int kc = 0; kc < kGnChunks; ++kc) {
+      sm100::mbar_wait(&H->bar[kc], 0);
+      const int a = min(nrows, kc * rows_per_chunk), b = min(nrows, (kc + 1) * rows_per_chunk);
+      // rows a..b-1, strided over the row lanes so that every lane's row set does not depend on the chunking
+      int r = a + ((M.my_row - a % M.rpb) + M.rpb) % M.rpb;
+      for (; r < b; r += M.rpb) {
+#pragma unroll
+        for (int k = 0; k < CPT; ++k) {
+          const int ch = (M.my_chunk + k * kGnThreads) * E;
+          if (ch < P.c) {
+            float v[E];
+            V16<T>::ld(ch < c1 ? slab1 + (size_t)r * c1 + ch : slab2 + (size_t)r * c2 + (ch - c1), v);
+#pragma unroll
+            for (int j = 0; j < E; ++j) { const float t = v[j] + av[k][j]; sum[k][j] += t; sq[k][j] = fmaf(t, t, sq[k][j]); }
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < CPT; ++k) {
+      const int ch = (M.my_chunk + k * kGnThreads) * E;
+      if (ch < P.c) {
+#pragma unroll
+        for (int j = 0; j < E; ++j) {
+          s_psum[M.my_row * P.c + ch + j] = sum[k][j];
+          s_psq[M.my_row * P.c + ch + j] = sq[k][j];
+        }
+      }
+    }
+  } else {
+    for (int kc = 0; kc < kGnChunks; ++kc) sm100::mbar_wait(&H->bar[kc], 0);
+  }
+  __syncthreads();
+  if (threadIdx.x < P.groups) {
+    float gs = 0.f, gq = 0.f;
+    for (int r = 0; r < M.rpb; ++r)
+      for (int ch = threadIdx.x * cpg; ch < (threadIdx.x + 1) * cpg; ++ch) {
+        gs += s_psum[r * P.c + ch];
+        gq += s_psq[r * P.c + ch];
+      }
+    H->red[2 * threadIdx.x] = gs;
+    H->red[2 * threadIdx.x + 1] = gq;
+  }
+  cluster.sync();
+  if (threadIdx.x < P.groups) {
+    double s = 0.0, q = 0.0;
+    for (int rk = 0; rk < cs; ++rk) {
+      const float* remote = cluster.map_shared_rank(H->red, rk);
+      s += (double)remote[2 * threadIdx.x];
+      q += (double)remote[2 * threadIdx.x + 1];
+    }
+    const double cnt = (double)P.hw * cpg;
+    const double mean = s / cnt;
+    double var = q / cnt - mean * mean;
+    if (var < 0.0) var = 0.0;
+    H->mean[threadIdx.x] = (float)mean;
+    H->rstd[threadIdx.x] = (float)(1.0 / sqrt(var + (double)P.eps));
+  }
+  cluster.sync();       // all remote reads done (no CTA may exit before); mean/rstd visible to the CTA
+  if (!M.active) return;
+  T* y = reinterpret_cast<T*>(P.y) + ((size_t)n * P.hw + r0) * P.c;
+  const T* gamma = reinterpret_cast<const T*>(P.gamma);
+  const T* beta = reinterpret_cast<const T*>(P.beta);
+  float scale[CPT][E], shift[CPT][E];
+#pragma unroll
+  for (int k = 0; k < CPT; ++k) {
+    const int ch = (M.my_chunk + k * kGnThreads) * E;
+    if (ch < P.c) {
+      float g[E], b[E], a[E];
+      V16<T>::ld(gamma + ch, g);
+      V16<T>::ld(beta + ch, b);
+#pragma unroll
+      for (int j = 0; j < E; ++j) a[j] = 0.f;
+      if (add) V16<T>::ld(add + ch, a);
+#pragma unroll
+      for (int j = 0; j < E; ++j) {
+        const int grp = (ch + j) / cpg;
+        scale[k][j] = H->rstd[grp] * g[j];
+        shift[k][j] = fmaf(a[j] - H->mean[grp], scale[k][j], b[j]);
+      }
+    }
+  }
+  for (int r = M.my_row; r < nrows; r += M.rpb) {
+#pragma unroll
+    for (int k = 0; k < CPT; ++k) {
+      const int ch = (M.my_chunk + k * kGnThreads) * E;
+      if (ch < P.c) {
+        float v[E];
+        V16<T>::ld(ch < c1 ? slab1 + (size_t)r * c1 + ch : slab2 + (size_t)r * c2 + (ch - c1), v);
+#pragma unroll
+        for (int j = 0; j < E; ++j) {
+          float t = fmaf(v[j], scale[k][j], shift[k][j]);
+          if (P.silu) t = t / (1.0f + __expf(-t));
+          v[j] = t;
+        }
+        V16<T>::st(y + (size_t)r * P.c + ch, v);
+      }
+    }
+  }
+}
+
+// Cluster size for the one-pass kernel (0: does not fit, use the two-pass kernels).
+static int gn_cluster_plan(int n, int hw, int c, int esize, int rpb, size_t* smem_bytes) {
+  const size_t budget = 200 * 1024;
+  for (int cs = 1; cs <= 16; cs *= 2) {
+    const int rows = (hw + cs - 1) / cs;
+    const size_t need = 1024 + (size_t)rows * c * esize + (size_t)2 * rpb * c * sizeof(float);
+    if (need <= budget) {
+      // enough CTAs to fill the chip if the sample can be cut further without making slabs tiny
+      int best = cs;
+      while (best < 16 && (long long)n * best < 2LL * num_sms() && (size_t)((hw + 2 * best - 1) / (2 * best)) * c * esize >= 16 * 1024) best *= 2;
+      const int rows_b = (hw + best - 1) / best;
+      *smem_bytes = 1024 + (size_t)rows_b * c * esize + (size_t)2 * rpb * c * sizeof(float);
+      return best;
+    }
+  }
+  return 0;
+}
+
+template <typename T, int CPT>
+static int gn_cluster_launch(GnParams& P, int cs, size_t smem, cudaStream_t st) {
+  static bool attr = false;
+  if (!attr) {
+    VF_CUDA_TRY(cudaFuncSetAttribute(gn_cluster_kernel<T, CPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    VF_CUDA_TRY(cudaFuncSetAttribute(gn_cluster_kernel<T, CPT>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    attr = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(P.n * cs), 1, 1);
+  cfg.blockDim = dim3(kGnThreads, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = (unsigned)cs;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  // can a cluster of this size and footprint be co-scheduled at all?  (validated once per size class)
+  static size_t ok_smem[17] = {0};
+  static bool bad[17] = {false};
+  if (bad[cs]) return -1;
+  if (smem > ok_smem[cs]) {
+    int n_clusters = 0;
+    if (cudaOccupancyMaxActiveClusters(&n_clusters, gn_cluster_kernel<T, CPT>, &cfg) != cudaSuccess || n_clusters < 1) {
+      cudaGetLastError();
+      bad[cs] = true;
+      return -1;                       // caller falls back to the two-pass kernels
+    }
+    ok_smem[cs] = smem;
+  }
+  return check_cuda(cudaLaunchKernelEx(&cfg, gn_cluster_kernel<T, CPT>, P), "gn_cluster_kernel launch");
+}
+
 // ================================================================================================
 // residual add + bias + LayerNorm (one warp per row)
 // ================================================================================================
@@ -364,7 +593,8 @@ extern "C" long long vf_group_norm_workspace_floats(int n, int hw, int groups) {
   int slabs, rps;
   if (n <= 0 || hw <= 0 || groups <= 0) return 0;
   vf::gn_plan(n, hw, &slabs, &rps);
-  return (long long)n * slabs * groups * 2;
+  (void)slabs;
+  return (long long)n * 64 * groups * 2;      // 64 = the most slabs gn_plan hands out (sample groups re-plan)
 }
 
 extern "C" int vf_group_norm_nhwc(const void* x, const void* add_nc, const void* gamma, const void* beta, void* y,
@@ -395,22 +625,65 @@ extern "C" int vf_group_norm_nhwc_cat(const void* x, int c1, const void* x2, int
   P.x2 = x2; P.c1 = x2 ? c1 : c;
   P.n = n; P.hw = hw; P.c = c; P.groups = groups; P.eps = eps; P.silu = silu;
   gn_plan(n, hw, &P.slabs, &P.rows_per_slab);
-  dim3 grid(P.slabs, n);
   cudaStream_t st = (cudaStream_t)stream;
   const int cpt = (c / e + kGnThreads - 1) / kGnThreads;
   const int chunks_ = c / e;
   const int rpb_ = kGnThreads / (chunks_ < kGnThreads ? chunks_ : kGnThreads);
   const size_t stats_smem = (size_t)2 * rpb_ * c * sizeof(float);
   if (stats_smem > 48 * 1024) return fail("vf_group_norm_nhwc: c=%d too wide", c);
+  {
+    // Experimental (VF_GN_ONEPASS=1): measured SLOWER than the L2-blocked two-pass below on B200 (0.49 vs
+    // 0.24 ms at n=96, 64x64x320 bf16): one 256-thread CTA per SM cannot hide its own shared-memory and MUFU
+    // latencies, and load / statistics / apply phases of a CTA do not overlap.
+    static int one_pass = -1;
+    if (one_pass < 0) { const char* e_ = getenv("VF_GN_ONEPASS"); one_pass = e_ ? atoi(e_) : 0; }
+    size_t cl_smem = 0;
+    const int cs = one_pass ? gn_cluster_plan(n, hw, c, dtype == VF_F32 ? 4 : 2, rpb_, &cl_smem) : 0;
+    if (cs > 0) {
+      P.rows_per_slab = (hw + cs - 1) / cs;
+      P.slabs = cs;
+#define VF_GNC(T)                                                                                 \
+      (cpt == 1 ? gn_cluster_launch<T, 1>(P, cs, cl_smem, st)                                      \
+                : cpt == 2 ? gn_cluster_launch<T, 2>(P, cs, cl_smem, st) : gn_cluster_launch<T, 3>(P, cs, cl_smem, st))
+      const int rc_cl = dtype == VF_F32 ? VF_GNC(float) : VF_GNC(__nv_bfloat16);
+#undef VF_GNC
+      if (rc_cl >= 0) return rc_cl;
+      gn_plan(n, hw, &P.slabs, &P.rows_per_slab);      // cluster shape not schedulable here: two-pass
+    }
+  }
+  // Experimental L2 blocking (VF_GN_L2_MB=<MiB>, default off): statistics and apply back to back over groups
+  // of samples small enough to stay in the 126 MB L2 between the passes.  Measured SLOWER on B200 (0.32-0.39 vs
+  // 0.24 ms at n=96, 64x64x320 bf16): six small launch pairs lose more to tails than the L2 hits return.
+  static long long l2_bytes = -1;
+  if (l2_bytes < 0) { const char* e_ = getenv("VF_GN_L2_MB"); l2_bytes = (e_ ? atoll(e_) : 0) << 20; }
+  const size_t per_sample = (size_t)hw * c * (dtype == VF_F32 ? 4 : 2);
+  int group = n;
+  if (l2_bytes > 0 && per_sample * n > (size_t)l2_bytes) {
+    group = (int)((size_t)l2_bytes / per_sample);
+    if (group < 1) group = 1;
+  }
+  const int c2_ = x2 ? c - P.c1 : 0;
+  const size_t es = dtype == VF_F32 ? 4 : 2;
 #define VF_GN_LAUNCH(T, K)                                        \
   do {                                                            \
     gn_stats_kernel<T, K><<<grid, kGnThreads, stats_smem, st>>>(P);        \
     gn_apply_kernel<T, K><<<grid, kGnThreads, 0, st>>>(P);        \
   } while (0)
-  if (dtype == VF_F32) {
-    if (cpt == 1) VF_GN_LAUNCH(float, 1); else if (cpt == 2) VF_GN_LAUNCH(float, 2); else VF_GN_LAUNCH(float, 3);
-  } else {
-    if (cpt == 1) VF_GN_LAUNCH(__nv_bfloat16, 1); else if (cpt == 2) VF_GN_LAUNCH(__nv_bfloat16, 2); else VF_GN_LAUNCH(__nv_bfloat16, 3);
+  for (int n0 = 0; n0 < n; n0 += group) {
+    const int gn = n - n0 < group ? n - n0 : group;
+    P.n = gn;
+    P.x = static_cast<const char*>(x) + (size_t)n0 * hw * P.c1 * es;
+    P.x2 = x2 ? static_cast<const char*>(x2) + (size_t)n0 * hw * c2_ * es : nullptr;
+    P.y = static_cast<char*>(y) + (size_t)n0 * hw * c * es;
+    P.add_nc = add_nc ? static_cast<const char*>(add_nc) + (size_t)n0 * c * es : nullptr;
+    gn_plan(gn, hw, &P.slabs, &P.rows_per_slab);
+    P.ws = workspace;       // reused: groups run in stream order
+    const dim3 grid(P.slabs, gn);
+    if (dtype == VF_F32) {
+      if (cpt == 1) VF_GN_LAUNCH(float, 1); else if (cpt == 2) VF_GN_LAUNCH(float, 2); else VF_GN_LAUNCH(float, 3);
+    } else {
+      if (cpt == 1) VF_GN_LAUNCH(__nv_bfloat16, 1); else if (cpt == 2) VF_GN_LAUNCH(__nv_bfloat16, 2); else VF_GN_LAUNCH(__nv_bfloat16, 3);
+    }
   }
 #undef VF_GN_LAUNCH
   return check_cuda(cudaGetLastError(), "group_norm kernels launch");
