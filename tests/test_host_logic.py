@@ -201,3 +201,49 @@ def test_vae_decoder_state_dict_keys_match_reference_golden():
     full = AutoencoderKLDecoder().state_dict()
     assert full["decoder.conv_in.weight"].shape == (512, 4, 3, 3) and full["decoder.mid.attn_1.q.weight"].shape == (512, 512, 1, 1)
     assert full["decoder.conv_out.weight"].shape == (3, 128, 3, 3) and len(full) == 140
+
+
+def test_flow_adapter_contract():
+    """image-resolution flow -> feature-pixel units at feature resolution."""
+    import torch
+    from vface_b200.scripts import temporal_flow as tf
+    # a constant translation of (+16, -8) image pixels at 512x512 is (+2, -1) feature pixels at 64x64
+    flow = torch.zeros(3, 2, 512, 512)
+    flow[:, 0], flow[:, 1] = 16.0, -8.0
+    out = tf.flow_to_feature_resolution(flow, 64)
+    assert tuple(out.shape) == (3, 2, 64, 64)
+    assert torch.allclose(out[:, 0], torch.full((3, 64, 64), 2.0)) and torch.allclose(out[:, 1], torch.full((3, 64, 64), -1.0))
+    # non-square: each component scales with its own axis; the reference's list-of-(1,2,H,W) form is accepted
+    lst = [torch.ones(1, 2, 256, 512) * 8.0 for _ in range(2)]
+    out = tf.flow_to_feature_resolution(lst, (64, 64))
+    assert torch.allclose(out[:, 0], torch.full((2, 64, 64), 1.0)) and torch.allclose(out[:, 1], torch.full((2, 64, 64), 2.0))
+    # already at feature resolution: unchanged
+    f64 = torch.randn(2, 2, 64, 64)
+    assert torch.equal(tf.flow_to_feature_resolution(f64, 64), f64)
+    # the authors' commented-out route: resize the frames, estimate at feature resolution
+    video = torch.randn(4, 3, 512, 512)
+    small = tf.resize_for_flow(video, 8)
+    assert tuple(small.shape) == (4, 3, 64, 64)
+    assert torch.equal(small, torch.nn.functional.interpolate(video, size=(64, 64), mode="bilinear", align_corners=False))
+
+
+def test_return_flow_batches_pairs_in_reference_order():
+    import torch
+    from vface_b200.scripts import temporal_flow as tf
+    calls = []
+
+    def estimator(img1, img2, num_flow_updates=20):
+        calls.append((img1.clone(), img2.clone(), num_flow_updates))
+        # a fake "flow": per-pair mean difference, broadcast; returned as RAFT's list of refinements
+        d = (img1 - img2).mean(dim=(1, 2, 3)).view(-1, 1, 1, 1).expand(-1, 2, img1.shape[-2], img1.shape[-1])
+        return [d * 0.5, d]
+
+    video = torch.randn(5, 3, 32, 32)
+    flow = tf.return_flow(video, estimator)
+    assert len(calls) == 1 and tuple(flow.shape) == (4, 2, 32, 32)
+    img1, img2, it = calls[0]
+    assert it == 20 and torch.equal(img1, video[1:]) and torch.equal(img2, video[:-1])     # compute_flow(frame2, frame1)
+    want = (video[1:] - video[:-1]).mean(dim=(1, 2, 3))
+    assert torch.allclose(flow[:, 0, 0, 0], want)
+    assert tuple(tf.return_flow(video, estimator, feature_size=8).shape) == (4, 2, 8, 8)
+    assert tf.return_flow(video[:1], estimator).shape[0] == 0

@@ -21,6 +21,12 @@ namespace vf {
 template <typename T> struct V16;   // 16-byte vector of T as floats
 template <> struct V16<float> {
   static constexpr int E = 4;
+  static __device__ __forceinline__ void unpack(const uint4& u, float (&v)[4]) {
+    v[0] = __uint_as_float(u.x); v[1] = __uint_as_float(u.y); v[2] = __uint_as_float(u.z); v[3] = __uint_as_float(u.w);
+  }
+  static __device__ __forceinline__ uint4 pack(const float (&v)[4]) {
+    return make_uint4(__float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]), __float_as_uint(v[3]));
+  }
   static __device__ __forceinline__ void ld(const float* p, float (&v)[4]) {
     float4 t = *reinterpret_cast<const float4*>(p);
     v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
@@ -31,6 +37,13 @@ template <> struct V16<float> {
 };
 template <> struct V16<__nv_bfloat16> {
   static constexpr int E = 8;
+  static __device__ __forceinline__ void unpack(const uint4& u, float (&v)[8]) {
+    v[0] = bf16lo(u.x); v[1] = bf16hi(u.x); v[2] = bf16lo(u.y); v[3] = bf16hi(u.y);
+    v[4] = bf16lo(u.z); v[5] = bf16hi(u.z); v[6] = bf16lo(u.w); v[7] = bf16hi(u.w);
+  }
+  static __device__ __forceinline__ uint4 pack(const float (&v)[8]) {
+    return make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+  }
   static __device__ __forceinline__ void ld(const __nv_bfloat16* p, float (&v)[8]) {
     uint4 u = *reinterpret_cast<const uint4*>(p);
     v[0] = bf16lo(u.x); v[1] = bf16hi(u.x); v[2] = bf16lo(u.y); v[3] = bf16hi(u.y);
@@ -40,6 +53,13 @@ template <> struct V16<__nv_bfloat16> {
     *reinterpret_cast<uint4*>(p) = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
   }
 };
+
+// SiLU.  fp32 path: IEEE division (reference precision).  bf16 path: the output is rounded to 8 mantissa
+// bits anyway, so the quotient goes through the fast reciprocal (MUFU.RCP) instead of the ~10-instruction
+// IEEE division sequence.
+template <typename T> __device__ __forceinline__ float silu_f(float t);
+template <> __device__ __forceinline__ float silu_f<float>(float t) { return t / (1.0f + __expf(-t)); }
+template <> __device__ __forceinline__ float silu_f<__nv_bfloat16>(float t) { return __fdividef(t, 1.0f + __expf(-t)); }
 
 // ================================================================================================
 // GroupNorm (NHWC)
@@ -97,7 +117,32 @@ gn_stats_kernel(const GnParams P) {
       for (int j = 0; j < E; ++j) { sum[k][j] = 0.f; sq[k][j] = 0.f; av[k][j] = 0.f; }
       if (add && ch < P.c) V16<T>::ld(add + ch, av[k]);
     }
-    for (int r = r0 + M.my_row; r < r1; r += M.rpb) {
+    // kRowUnroll rows per trip: that many independent 16-byte loads in flight per thread and chunk (one load
+    // per trip left the SM far short of the ~44 KB it must keep in flight to cover HBM latency)
+    constexpr int kRowUnroll = CPT == 1 ? 4 : 2;
+    int r = r0 + M.my_row;
+    for (; r + (kRowUnroll - 1) * M.rpb < r1; r += kRowUnroll * M.rpb) {
+#pragma unroll
+      for (int k = 0; k < CPT; ++k) {
+        const int ch = (M.my_chunk + k * kGnThreads) * E;
+        if (ch < P.c) {
+          uint4 raw[kRowUnroll];
+#pragma unroll
+          for (int u = 0; u < kRowUnroll; ++u) {
+            const size_t rr = (size_t)(r + u * M.rpb);
+            raw[u] = ld_nc_v4(ch < P.c1 ? x + rr * P.c1 + ch : x2 + rr * c2 + (ch - P.c1));
+          }
+#pragma unroll
+          for (int u = 0; u < kRowUnroll; ++u) {
+            float v[E];
+            V16<T>::unpack(raw[u], v);
+#pragma unroll
+            for (int j = 0; j < E; ++j) { const float t = v[j] + av[k][j]; sum[k][j] += t; sq[k][j] = fmaf(t, t, sq[k][j]); }
+          }
+        }
+      }
+    }
+    for (; r < r1; r += M.rpb) {
 #pragma unroll
       for (int k = 0; k < CPT; ++k) {
         const int ch = (M.my_chunk + k * kGnThreads) * E;
@@ -187,7 +232,35 @@ gn_apply_kernel(const GnParams P) {
       }
     }
   }
-  for (int r = r0 + M.my_row; r < r1; r += M.rpb) {
+  constexpr int kRowUnroll = CPT == 1 ? 4 : 2;
+  int r = r0 + M.my_row;
+  for (; r + (kRowUnroll - 1) * M.rpb < r1; r += kRowUnroll * M.rpb) {
+#pragma unroll
+    for (int k = 0; k < CPT; ++k) {
+      const int ch = (M.my_chunk + k * kGnThreads) * E;
+      if (ch < P.c) {
+        uint4 raw[kRowUnroll];
+#pragma unroll
+        for (int u = 0; u < kRowUnroll; ++u) {
+          const size_t rr = (size_t)(r + u * M.rpb);
+          raw[u] = ld_nc_v4(ch < P.c1 ? x + rr * P.c1 + ch : x2 + rr * c2 + (ch - P.c1));
+        }
+#pragma unroll
+        for (int u = 0; u < kRowUnroll; ++u) {
+          float v[E];
+          V16<T>::unpack(raw[u], v);
+#pragma unroll
+          for (int j = 0; j < E; ++j) {
+            float t = fmaf(v[j], scale[k][j], shift[k][j]);
+            if (P.silu) t = silu_f<T>(t);
+            v[j] = t;
+          }
+          st_na_v4(y + (size_t)(r + u * M.rpb) * P.c + ch, V16<T>::pack(v));
+        }
+      }
+    }
+  }
+  for (; r < r1; r += M.rpb) {
 #pragma unroll
     for (int k = 0; k < CPT; ++k) {
       const int ch = (M.my_chunk + k * kGnThreads) * E;
@@ -197,7 +270,7 @@ gn_apply_kernel(const GnParams P) {
 #pragma unroll
         for (int j = 0; j < E; ++j) {
           float t = fmaf(v[j], scale[k][j], shift[k][j]);
-          if (P.silu) t = t / (1.0f + __expf(-t));
+          if (P.silu) t = silu_f<T>(t);
           v[j] = t;
         }
         V16<T>::st(y + (size_t)r * P.c + ch, v);
@@ -531,21 +604,59 @@ add_layer_norm_kernel(const LnParams P) {
 // ================================================================================================
 // GEGLU and residual add
 // ================================================================================================
+// exact (erf) GELU.  fp32 path: libdevice erff.  bf16 path: Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7, far
+// below the 4e-3 spacing of the bf16 result) -- one MUFU.RCP, one MUFU.EX2 and a degree-5 Horner chain instead
+// of erff's ~30 instructions, which made the kernel ALU-bound (48 bytes per 8 erff calls).
+template <typename T> __device__ __forceinline__ float gelu_f(float g);
+template <> __device__ __forceinline__ float gelu_f<float>(float g) { return 0.5f * g * (1.0f + erff(g * 0.70710678118654752f)); }
+template <> __device__ __forceinline__ float gelu_f<__nv_bfloat16>(float g) {
+  const float x = fabsf(g) * 0.70710678118654752f;
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, x, 1.0f));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  const float e = p * t * exp2f(-1.4426950408889634f * x * x);      // 1 - erf(|x|)
+  const float erf_abs = 1.0f - e;
+  return 0.5f * g * (1.0f + copysignf(erf_abs, g));
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256)
 geglu_kernel(const T* __restrict__ h, T* __restrict__ out, long long rows, int k, long long ld_h) {
   constexpr int E = V16<T>::E;
   const int chunks = k / E;
   const long long total = rows * chunks;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const long long r = i / chunks;
-    const int ch = (int)(i - r * chunks) * E;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  // two independent chunks per trip (four 16-byte loads in flight per thread)
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += 2 * stride) {
+    const long long i1 = i + stride;
+    const bool two = i1 < total;
+    long long r0, r1;
+    if (total < 0x7fffffffLL) {        // 32-bit index arithmetic whenever it fits (64-bit division is ~40 instructions)
+      r0 = (unsigned)i / (unsigned)chunks;
+      r1 = two ? (unsigned)i1 / (unsigned)chunks : r0;
+    } else {
+      r0 = i / chunks;
+      r1 = two ? i1 / chunks : r0;
+    }
+    const int c0 = (int)(i - r0 * chunks) * E;
+    const int c1 = two ? (int)(i1 - r1 * chunks) * E : c0;
+    const uint4 ua0 = ld_nc_v4(h + r0 * ld_h + c0), ug0 = ld_nc_v4(h + r0 * ld_h + k + c0);
+    const uint4 ua1 = ld_nc_v4(h + r1 * ld_h + c1), ug1 = ld_nc_v4(h + r1 * ld_h + k + c1);
     float a[E], g[E];
-    V16<T>::ld(h + r * ld_h + ch, a);
-    V16<T>::ld(h + r * ld_h + k + ch, g);
+    V16<T>::unpack(ua0, a);
+    V16<T>::unpack(ug0, g);
 #pragma unroll
-    for (int j = 0; j < E; ++j) a[j] *= 0.5f * g[j] * (1.0f + erff(g[j] * 0.70710678118654752f));   // exact (erf) GELU
-    V16<T>::st(out + r * (long long)k + ch, a);
+    for (int j = 0; j < E; ++j) a[j] *= gelu_f<T>(g[j]);
+    st_na_v4(out + r0 * (long long)k + c0, V16<T>::pack(a));
+    if (two) {
+      V16<T>::unpack(ua1, a);
+      V16<T>::unpack(ug1, g);
+#pragma unroll
+      for (int j = 0; j < E; ++j) a[j] *= gelu_f<T>(g[j]);
+      st_na_v4(out + r1 * (long long)k + c1, V16<T>::pack(a));
+    }
   }
 }
 
