@@ -1,6 +1,6 @@
 """Kernel microbenchmarks: BASELINE.json configs 3 (attention) and 4 (FSAI, flow warp) + CFG/DDIM.
 
-    python benchmarks/bench_kernels.py [--only attn|fsai|warp|ddim|glue] [--iters 20] [--json out.json]
+    python benchmarks/bench_kernels.py [--only attn|fsai|warp|ddim|glue|gemm] [--iters 20] [--json out.json]
 
 Timing: CUDA events on the launching (current) stream, >= 3 warm-up launches, an L2 flush (write of a
 256 MiB buffer) before every timed launch.  Rooflines use /root/repo/MEASURED_PEAKS.json when present,
@@ -165,6 +165,26 @@ def bench_glue(res, iters):
         3.0 * 96 * 4096 * 640 * e)
 
 
+def bench_gemm(res, iters):
+    """Fused tcgen05 GEMM+GEGLU against library GEMM + geglu kernel at the three feed-forward shapes of a step."""
+    import torch.nn.functional as F
+    pk = peaks()
+    g = torch.Generator(device="cuda").manual_seed(0)
+    for rows, k, n in ((96 * 4096, 320, 1280), (96 * 1024, 640, 2560), (96 * 256, 1280, 5120)):
+        x = torch.randn(rows, k, device="cuda", generator=g).bfloat16()
+        w = (torch.randn(2 * n, k, device="cuda", generator=g) / k ** 0.5).bfloat16()
+        b = torch.randn(2 * n, device="cuda", generator=g).bfloat16()
+        flops = 2.0 * rows * k * 2 * n
+        for name, fn in (("fused linear+geglu (tcgen05)", lambda: ops.linear_geglu(x, w, b)),
+                         ("cuBLAS linear + vf_geglu", lambda: ops.geglu(F.linear(x, w, b))),
+                         ("cuBLAS linear alone", lambda: F.linear(x, w, b))):
+            med, best = time_kernel(fn, iters)
+            tf = flops / (med * 1e-3) / 1e12
+            full = f"{name} rows={rows} k={k} n={n}"
+            res.append(dict(kernel=full, ms=med, ms_best=best, tflops=tf, frac_burst=tf / pk["tc"], bound="tensor", peaks=pk["src"]))
+            print(f"{full:62s} {med:8.3f} ms  {tf:8.1f} TFLOP/s  {100 * tf / pk['tc']:5.1f}% of {pk['src']} burst peak")
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default="")
@@ -173,7 +193,7 @@ def main():
     a = ap.parse_args()
     res = []
     print(torch.cuda.get_device_name(0), "| peaks:", peaks())
-    for name, fn in (("attn", bench_attn), ("fsai", bench_fsai), ("warp", bench_warp), ("ddim", bench_ddim), ("glue", bench_glue)):
+    for name, fn in (("attn", bench_attn), ("fsai", bench_fsai), ("warp", bench_warp), ("ddim", bench_ddim), ("glue", bench_glue), ("gemm", bench_gemm)):
         if a.only and a.only != name:
             continue
         fn(res, a.iters)

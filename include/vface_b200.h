@@ -28,7 +28,7 @@ extern "C" {
 #define VF_F32 0
 #define VF_BF16 1
 
-#define VF_ABI_VERSION 3
+#define VF_ABI_VERSION 4
 
 /* ABI version of the loaded library (== VF_ABI_VERSION). */
 int vf_abi_version(void);
@@ -169,6 +169,16 @@ int vf_add_layer_norm(const void* x, const void* y, const void* bias, long long 
  * Replaces GEGLU.forward (ldm/modules/attention.py:43-45).
  */
 int vf_geglu(const void* h, void* out, long long rows, int k, long long ld_h, int dtype, void* stream);
+
+/*
+ * Feed-forward up-projection with the GEGLU gate fused into the GEMM epilogue (tcgen05 tensor cores):
+ *   out[r, 0:n] = (x[r] . Wv^T + bv) * gelu(x[r] . Wg^T + bg),  w = [Wv ; Wg] (2n, k) row-major, bias (2n) or NULL.
+ * Replaces GEGLU.forward (ldm/modules/attention.py:37-45: proj -> chunk(2) -> x * gelu(gate)); the (rows, 2n)
+ * projection is never written to memory.  bf16 only (the fp32 path keeps library GEMM + vf_geglu);
+ * k % 8 == 0, n % 128 == 0; x row stride ld_x elements, out is (rows, n) contiguous.
+ */
+int vf_linear_geglu(const void* x, const void* w, const void* bias, void* out,
+                    long long rows, int k, int n, long long ld_x, int dtype, void* stream);
 
 /*
  * out = a + b + bias (b, bias optional; bias rows as in vf_add_layer_norm).  Residual adds and the

@@ -321,3 +321,50 @@ def test_errors_are_loud():
     y = torch.zeros(1, 8, 96, device=_dev())
     with pytest.raises(RuntimeError):
         ops.fsai_blend(y, y.clone(), 0.8)   # d=96 = 2^5 * 3
+
+
+# ------------------------------------------------------------------------------------------------
+# fused GEMM + GEGLU (tcgen05)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("rows,k,n", [(4096, 320, 1280), (1024 + 37, 640, 2560), (256, 1280, 5120), (100, 64, 128)])
+def test_linear_geglu_vs_reference_form(rows, k, n):
+    """GEGLU.forward (attention.py:37-45): proj -> chunk(2) -> x * gelu(gate), in fp64 on the bf16-rounded
+    operands, against the fused tcgen05 GEMM; ragged row counts exercise the TMA zero fill and the row mask."""
+    from vface_b200 import ops
+    g = torch.Generator().manual_seed(rows + k)
+    x = torch.randn(rows, k, generator=g).bfloat16()
+    w = (torch.randn(2 * n, k, generator=g) / k ** 0.5).bfloat16()
+    b = (torch.randn(2 * n, generator=g) * 0.1).bfloat16()
+    proj = x.double() @ w.double().t() + b.double()
+    val, gate = proj.chunk(2, dim=-1)
+    want = val * torch.nn.functional.gelu(gate)
+    dev = _dev()
+    assert ops.linear_geglu_supported(x.to(dev), w.to(dev))
+    got = ops.linear_geglu(x.to(dev), w.to(dev), b.to(dev)).double().cpu()
+    assert tuple(got.shape) == (rows, n)
+    err = (got - want).abs().max().item()
+    assert err < BF16_TOL * max(1.0, want.abs().max().item() / 4), err
+    got_nb = ops.linear_geglu(x.to(dev), w.to(dev), None).double().cpu()
+    proj = x.double() @ w.double().t()
+    val, gate = proj.chunk(2, dim=-1)
+    assert (got_nb - val * torch.nn.functional.gelu(gate)).abs().max().item() < BF16_TOL * max(1.0, want.abs().max().item() / 4)
+
+
+def test_linear_geglu_matches_unfused_module_path():
+    """The GEGLU module gives the same result (to bf16 round-off) through the fused kernel and through library
+    GEMM + vf_geglu (VF_FUSED_GEGLU=0)."""
+    import os
+    from vface_b200.ldm.modules.attention import GEGLU
+    torch.manual_seed(3)
+    m = GEGLU(320, 1280).to(_dev()).bfloat16()
+    x = torch.randn(3, 4096, 320, device=_dev()).bfloat16()
+    fused = m(x)
+    os.environ["VF_FUSED_GEGLU"] = "0"
+    try:
+        plain = m(x)
+    finally:
+        del os.environ["VF_FUSED_GEGLU"]
+    assert fused.shape == plain.shape
+    # the unfused path rounds the projection to bf16 before gating; the fused one gates the fp32 accumulator
+    assert (fused.float() - plain.float()).abs().max().item() < 4e-2
+    assert ((fused.float() - plain.float()).norm() / plain.float().norm()).item() < 5e-3

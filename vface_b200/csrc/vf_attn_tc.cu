@@ -46,6 +46,7 @@ struct AttnTcParams {
   long long ld_o;
   int heads, n_q, n_kv, n_kv2, d, d_pad, kb;   // kb = ceil(d / 64) 64-wide head-dim blocks
   float scale_log2;                            // scale * log2(e)
+  int spin;                                    // tuning knob: poll instead of suspending on the softmax-side barriers
 };
 
 constexpr int kMaxStages = 4;
@@ -188,12 +189,14 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         for (int j = 0; j < n_tiles; ++j) {
           const int st = j % kStages;
           if (kSplitP && j + 1 < n_tiles) {
-            mbar_wait(&bars.s_free, (uint32_t)j & 1);      // S_j is in the softmax threads' registers
+            if (P.spin & 2) mbar_wait_spin(&bars.s_free, (uint32_t)j & 1);
+            else mbar_wait(&bars.s_free, (uint32_t)j & 1);      // S_j is in the softmax threads' registers
             tc_fence_after();
             issue_qk(j + 1);
           }
           mbar_wait(&bars.v_full[st], (uint32_t)(j / kStages) & 1);
-          mbar_wait(&bars.p_full, (uint32_t)j & 1);        // P_j in TMEM (over S_j), O rescaled if needed
+          if (P.spin & 2) mbar_wait_spin(&bars.p_full, (uint32_t)j & 1);
+          else mbar_wait(&bars.p_full, (uint32_t)j & 1);        // P_j in TMEM, O rescaled if needed
           tc_fence_after();
 #pragma unroll 1
           for (int s = 0; s < BN / 16; ++s) {
@@ -228,7 +231,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
       const int valid = min(BN, (seg2 ? P.n_kv2 : P.n_kv) - row0);
 
       // S_j complete; the commit also covers PV_{j-1}, so P/O are ours again.
-      mbar_wait(&bars.s_full, (uint32_t)j & 1);
+      if (P.spin) mbar_wait_spin(&bars.s_full, (uint32_t)j & 1);
+      else mbar_wait(&bars.s_full, (uint32_t)j & 1);
       tc_fence_after();
       uint32_t sr[BN / 32][32];
 #pragma unroll
@@ -311,7 +315,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
             pk[cc * 16 + i / 2 + 1] = pack_bf16(p2, p3);
           }
         if (kSplitP && g == 0 && j > 0) {              // PV_{j-1} still reads P (and writes O) until its commit
-          mbar_wait(&bars.p_empty, (uint32_t)(j - 1) & 1);
+          if (P.spin) mbar_wait_spin(&bars.p_empty, (uint32_t)(j - 1) & 1);
+          else mbar_wait(&bars.p_empty, (uint32_t)(j - 1) & 1);
           tc_fence_after();
         }
         tmem_st_x32(tm_p + lane_off + g * 32, pk);
@@ -437,6 +442,11 @@ int launch_attn_tc(const void* q, const void* k, const void* v, void* o, int bat
   P.heads = heads; P.n_q = n_q; P.n_kv = n_kv; P.n_kv2 = has2 ? n_kv2 : 0;
   P.d = d; P.d_pad = (d + 15) / 16 * 16; P.kb = (d + 63) / 64;
   P.scale_log2 = scale * 1.4426950408889634f;
+  {
+    static int spin = -1;
+    if (spin < 0) { const char* e = getenv("VF_ATTN_SPIN"); spin = e ? atoi(e) : 0; }
+    P.spin = spin;
+  }
   const int bn = 64;
   CUtensorMap mq, mk, mv, mk2, mv2;
   if (int rc = make_map(&mq, q, batch, heads, n_q, d, ld_q, kBM)) return rc;

@@ -41,7 +41,11 @@ class GEGLU(nn.Module):
         self.proj = nn.Linear(dim_in, dim_out * 2)
 
     def forward(self, x):
-        return ops.geglu(self.proj(x))        # x * gelu(gate) in one pass (reference :43-45)
+        # bf16: projection + gate in ONE tcgen05 GEMM kernel (the (rows, 2*dim_out) projection never reaches HBM);
+        # fp32 / odd shapes: library GEMM, then x * gelu(gate) in one pass (reference :43-45)
+        if ops.linear_geglu_supported(x, self.proj.weight):
+            return ops.linear_geglu(x.contiguous(), self.proj.weight, self.proj.bias)
+        return ops.geglu(self.proj(x))
 
 
 class FeedForward(nn.Module):

@@ -6,6 +6,8 @@ provider here; there is no eager/CPU fallback -- CPU tensors or a missing librar
 """
 from __future__ import annotations
 
+import os
+
 from typing import Optional, Sequence, Union
 
 import torch
@@ -329,6 +331,33 @@ def geglu(h: torch.Tensor) -> torch.Tensor:
     lib = _lib.load()
     rc = lib.vf_geglu(h.data_ptr(), out.data_ptr(), rows, k, two_k, _code(h), _stream(h))
     _lib.check(rc, "vf_geglu")
+    _count()
+    return out
+
+
+def linear_geglu_supported(x: torch.Tensor, weight: torch.Tensor) -> bool:
+    """Shapes/dtypes the fused tcgen05 GEMM+GEGLU kernel takes (everything else: library GEMM + geglu)."""
+    two_n, k = weight.shape
+    return (x.dtype == torch.bfloat16 and weight.dtype == torch.bfloat16 and x.is_cuda and k % 64 == 0
+            and two_n % 256 == 0 and x.shape[-1] == k and os.environ.get("VF_FUSED_GEGLU", "1") != "0")
+
+
+def linear_geglu(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor]) -> torch.Tensor:
+    """GEGLU.forward (ldm/modules/attention.py:37-45) as ONE kernel: (x @ Wv^T + bv) * gelu(x @ Wg^T + bg) with
+    weight = [Wv ; Wg] (2n, k); the (rows, 2n) projection never reaches HBM."""
+    _need_cuda(x, weight, bias)
+    if not x.is_contiguous() or not weight.is_contiguous():
+        raise ValueError("linear_geglu: x and weight must be contiguous")
+    two_n, k = weight.shape
+    n = two_n // 2
+    rows = x.numel() // k
+    if bias is not None and (bias.dtype != x.dtype or bias.numel() != two_n or not bias.is_contiguous()):
+        raise ValueError("linear_geglu: bad bias")
+    out = torch.empty(x.shape[:-1] + (n,), dtype=x.dtype, device=x.device)
+    lib = _lib.load()
+    rc = lib.vf_linear_geglu(x.data_ptr(), weight.data_ptr(), bias.data_ptr() if bias is not None else None, out.data_ptr(),
+                             rows, k, n, k, _code(x), _stream(x))
+    _lib.check(rc, "vf_linear_geglu")
     _count()
     return out
 
