@@ -19,6 +19,12 @@
 //               (A&S 7.1.26 erf, |err| < 5e-7), bf16x2 pack, 16-byte stores (each thread 64 contiguous bytes).
 // Tiles are walked n-fastest, so the CTAs running at any instant share one or two A row-blocks through L2
 // and W (a few MB) stays L2-resident.
+//
+// kWResident (k <= 320, the 64x64 level): at k = 320 a tile moves 240 KB through L2 for 2560 tensor cycles of
+// work -- 94 B/clk/SM against the ~42 B/clk/SM that the L2 can feed 148 SMs -- and the streaming kernel is
+// L2-bound (measured 8.5 TB/s of L2 reads).  The value+gate weight tile of ONE n-block for ALL of k is only
+// 160 KB, so each CTA keeps it in shared memory for its whole life, walks the m-blocks of its n-block and
+// streams only A (80 KB per tile).
 #include "vf_common.cuh"
 #include "vf_sm100.cuh"
 
@@ -33,7 +39,7 @@ constexpr int kGemmThreads = 256;
 constexpr int kGemmBM = 128;          // rows per tile
 constexpr int kGemmBN = 128;          // OUTPUT columns per tile (256 accumulator columns: value + gate)
 constexpr int kGemmBK = 64;           // k-block: 64 bf16 = one 128-byte swizzled row
-constexpr int kGemmStages = 3;
+constexpr int kGemmStages = 4;
 constexpr uint32_t kATileBytes = kGemmBM * kGemmBK * 2;          // 16 KB
 constexpr uint32_t kBTileBytes = 2 * kGemmBN * kGemmBK * 2;      // 32 KB (value rows, then gate rows)
 constexpr uint32_t kStageBytes = kATileBytes + kBTileBytes;
@@ -49,7 +55,34 @@ struct GemmGegluParams {
 struct __align__(8) GemmBarriers {
   uint64_t full[kGemmStages], empty[kGemmStages];
   uint64_t acc_full[2], acc_empty[2];
+  uint64_t w_full;
   uint32_t tmem_base;
+};
+
+// tile walk.  streaming: tile = blockIdx.x + i*gridDim.x, n-fastest.  W-resident: the CTA owns n-block
+// blockIdx.x % n_blocks and walks m-blocks group, group + groups, ... (groups = gridDim.x / n_blocks).
+template <bool kWResident>
+struct TileWalk {
+  long long cur, end, step;
+  int nb_fixed, n_blocks;
+  __device__ TileWalk(const GemmGegluParams& P) {
+    n_blocks = P.n_blocks;
+    if (kWResident) {
+      nb_fixed = blockIdx.x % P.n_blocks;
+      cur = blockIdx.x / P.n_blocks;
+      step = gridDim.x / P.n_blocks;
+      end = P.m_blocks;
+    } else {
+      nb_fixed = 0;
+      cur = blockIdx.x;
+      step = gridDim.x;
+      end = (long long)P.m_blocks * P.n_blocks;
+    }
+  }
+  __device__ bool valid() const { return cur < end; }
+  __device__ void next() { cur += step; }
+  __device__ int mb() const { return kWResident ? (int)cur : (int)(cur / n_blocks); }
+  __device__ int nb() const { return kWResident ? nb_fixed : (int)(cur % n_blocks); }
 };
 
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
@@ -62,36 +95,64 @@ __device__ __forceinline__ void named_bar_sync(int id, int threads) {
   asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(threads) : "memory");
 }
 
-// exact-GELU through the Abramowitz-Stegun 7.1.26 erf (same form as vf_norm.cu's bf16 GEGLU)
-__device__ __forceinline__ float gelu_as(float g) {
-  const float x = fabsf(g) * 0.70710678118654752f;
-  const float t = __fdividef(1.0f, fmaf(0.3275911f, x, 1.0f));
-  float p = fmaf(1.061405429f, t, -1.453152027f);
-  p = fmaf(p, t, 1.421413741f);
-  p = fmaf(p, t, -0.284496736f);
-  p = fmaf(p, t, 0.254829592f);
-  const float e = p * t * exp2f(-1.4426950408889634f * x * x);
-  return 0.5f * g * (1.0f + copysignf(1.0f - e, g));
+// v * gelu(g) for a PAIR of elements, exact (erf) GELU through Abramowitz-Stegun 7.1.26 (|err| < 5e-7), written
+// for the epilogue's issue budget: every fp32 operation is a packed FFMA2/FMUL2/FADD2 over the pair, the two
+// transcendental steps are one MUFU each (rcp.approx, ex2.approx), |g| and copysign are single LOP3s:
+// ~12 issue slots per element against 27 for the scalar libdevice form (which made the epilogue, not the
+// tensor pipe, the bound at k = 320).
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float ex2_approx_ftz(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float2 splat2(float c) { return make_float2(c, c); }
+
+__device__ __forceinline__ float2 geglu_pair(float2 v, float2 g) {
+  const float2 a = make_float2(fabsf(g.x), fabsf(g.y));
+  const float2 den = __ffma2_rn(a, splat2(0.3275911f * 0.70710678118654752f), splat2(1.0f));
+  const float2 t = make_float2(rcp_approx(den.x), rcp_approx(den.y));
+  float2 p = __ffma2_rn(splat2(1.061405429f), t, splat2(-1.453152027f));
+  p = __ffma2_rn(p, t, splat2(1.421413741f));
+  p = __ffma2_rn(p, t, splat2(-0.284496736f));
+  p = __ffma2_rn(p, t, splat2(0.254829592f));
+  const float2 xa = __fmul2_rn(__fmul2_rn(g, g), splat2(-0.5f * 1.4426950408889634f));     // -(g/sqrt2)^2 * log2(e)
+  const float2 ex = make_float2(ex2_approx_ftz(xa.x), ex2_approx_ftz(xa.y));
+  const float2 e = __fmul2_rn(__fmul2_rn(p, t), ex);                                        // 1 - erf(|g|/sqrt2)
+  const float2 m = __ffma2_rn(e, splat2(-1.0f), splat2(1.0f));                              // erf(|g|/sqrt2)
+  const float2 sg = make_float2(copysignf(m.x, g.x), copysignf(m.y, g.y));
+  const float2 hg = __fmul2_rn(g, splat2(0.5f));
+  return __fmul2_rn(v, __ffma2_rn(hg, sg, hg));
 }
 
+template <bool kWResident>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_geglu_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
                   const GemmGegluParams P) {
+  // all shared memory is dynamic (the W-resident layout uses the 227 KB to within 1 KB):
+  //   [pad to 1024] | resident W (k_blocks x 32 KB, W-resident only) | ring (kGemmStages stages) | barriers | bias
   extern __shared__ unsigned char gemm_smem[];
-  __shared__ GemmBarriers bars;
-  __shared__ __align__(16) float s_bias[2][2 * kGemmBN];   // per accumulator set: value bias [0,128), gate bias [128,256)
-
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const uint32_t dyn_base = smem_u32(gemm_smem);
   const uint32_t tile_base = (dyn_base + 1023u) & ~1023u;
   unsigned char* tiles = gemm_smem + (tile_base - dyn_base);
+  const size_t tile_bytes = (kWResident ? (size_t)P.k_blocks * kBTileBytes + (size_t)kGemmStages * kATileBytes
+                                        : (size_t)kGemmStages * kStageBytes);
+  GemmBarriers& bars = *reinterpret_cast<GemmBarriers*>(tiles + tile_bytes);
+  // per accumulator set: value bias [0,128), gate bias [128,256)
+  float (*s_bias)[2 * kGemmBN] = reinterpret_cast<float (*)[2 * kGemmBN]>(tiles + tile_bytes + 128);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kGemmStages; ++s) {
       mbar_init(&bars.full[s], 1);
       mbar_init(&bars.empty[s], 1);
     }
+    mbar_init(&bars.w_full, 1);
     for (int a = 0; a < 2; ++a) {
       mbar_init(&bars.acc_full[a], 1);
       mbar_init(&bars.acc_empty[a], 4);            // one arrival per epilogue warp
@@ -103,7 +164,10 @@ gemm_geglu_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = bars.tmem_base;
-  const long long n_tiles = (long long)P.m_blocks * P.n_blocks;
+  // shared memory: [resident W: k_blocks x 32 KB] | A(+W) ring
+  unsigned char* w_res = tiles;
+  unsigned char* ring = kWResident ? tiles + (size_t)P.k_blocks * kBTileBytes : tiles;
+  constexpr uint32_t kRingStage = kWResident ? kATileBytes : kStageBytes;
 
   if (warp == 0) {
     // =========================== TMA producer ====================================================
@@ -111,17 +175,28 @@ gemm_geglu_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       tma_prefetch_desc(&map_a);
       tma_prefetch_desc(&map_w);
       uint32_t it = 0;
-      for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int mb = (int)(tile / P.n_blocks), nb = (int)(tile - (long long)mb * P.n_blocks);
+      TileWalk<kWResident> tw(P);
+      if (kWResident && tw.valid()) {
+        mbar_arrive_expect_tx(&bars.w_full, (uint32_t)P.k_blocks * kBTileBytes);
+        for (int kb = 0; kb < P.k_blocks; ++kb) {
+          unsigned char* wd = w_res + (size_t)kb * kBTileBytes;
+          tma_load_2d(wd, &map_w, &bars.w_full, kb * kGemmBK, tw.nb() * kGemmBN);
+          tma_load_2d(wd + kBTileBytes / 2, &map_w, &bars.w_full, kb * kGemmBK, P.n + tw.nb() * kGemmBN);
+        }
+      }
+      for (; tw.valid(); tw.next()) {
+        const int mb = tw.mb(), nb = tw.nb();
         for (int kb = 0; kb < P.k_blocks; ++kb, ++it) {
           const int s = it % kGemmStages;
           const uint32_t use = it / kGemmStages;
           mbar_wait(&bars.empty[s], (use & 1) ^ 1);
-          mbar_arrive_expect_tx(&bars.full[s], kStageBytes);
-          unsigned char* st = tiles + (size_t)s * kStageBytes;
+          mbar_arrive_expect_tx(&bars.full[s], kRingStage);
+          unsigned char* st = ring + (size_t)s * kRingStage;
           tma_load_2d(st, &map_a, &bars.full[s], kb * kGemmBK, mb * kGemmBM);
-          tma_load_2d(st + kATileBytes, &map_w, &bars.full[s], kb * kGemmBK, nb * kGemmBN);
-          tma_load_2d(st + kATileBytes + kBTileBytes / 2, &map_w, &bars.full[s], kb * kGemmBK, P.n + nb * kGemmBN);
+          if (!kWResident) {
+            tma_load_2d(st + kATileBytes, &map_w, &bars.full[s], kb * kGemmBK, nb * kGemmBN);
+            tma_load_2d(st + kATileBytes + kBTileBytes / 2, &map_w, &bars.full[s], kb * kGemmBK, P.n + nb * kGemmBN);
+          }
         }
       }
     }
@@ -130,7 +205,12 @@ gemm_geglu_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     if (lane == 0) {
       const uint32_t idesc = make_idesc_bf16(kGemmBM, 2 * kGemmBN, false);
       uint32_t it = 0, ti = 0;
-      for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ti) {
+      TileWalk<kWResident> tw(P);
+      if (kWResident && tw.valid()) {
+        mbar_wait(&bars.w_full, 0);
+        tc_fence_after();
+      }
+      for (; tw.valid(); tw.next(), ++ti) {
         const uint32_t ab = ti & 1, ause = ti >> 1;
         mbar_wait(&bars.acc_empty[ab], (ause & 1) ^ 1);     // epilogue drained this accumulator set
         tc_fence_after();
@@ -139,8 +219,8 @@ gemm_geglu_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
           const int s = it % kGemmStages;
           mbar_wait(&bars.full[s], (it / kGemmStages) & 1);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(tiles + (size_t)s * kStageBytes);
-          const uint32_t b_addr = a_addr + kATileBytes;
+          const uint32_t a_addr = smem_u32(ring + (size_t)s * kRingStage);
+          const uint32_t b_addr = kWResident ? smem_u32(w_res + (size_t)kb * kBTileBytes) : a_addr + kATileBytes;
 #pragma unroll
           for (int ks = 0; ks < kGemmBK / 16; ++ks) {
             const uint64_t da = make_smem_desc_sw128(a_addr + ks * 32, 16, 1024);
@@ -158,14 +238,18 @@ gemm_geglu_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
     const int et = threadIdx.x - 128;                        // 0..127
     uint32_t ti = 0;
-    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ti) {
-      const int mb = (int)(tile / P.n_blocks), nb = (int)(tile - (long long)mb * P.n_blocks);
+    for (TileWalk<kWResident> tw(P); tw.valid(); tw.next(), ++ti) {
+      const int mb = tw.mb(), nb = tw.nb();
       const uint32_t ab = ti & 1, ause = ti >> 1;
       // bias slice of this tile (double-buffered with the accumulator set: the previous user of s_bias[ab]
       // finished two tiles ago and every epilogue thread passed a named barrier since)
-      s_bias[ab][et] = P.bias ? __bfloat162float(P.bias[nb * kGemmBN + et]) : 0.0f;
-      s_bias[ab][kGemmBN + et] = P.bias ? __bfloat162float(P.bias[P.n + nb * kGemmBN + et]) : 0.0f;
-      named_bar_sync(1, 128);
+      // (W-resident: the n-block never changes, one set filled on the first tile)
+      const uint32_t bs = kWResident ? 0u : ab;
+      if (!kWResident || ti == 0) {
+        s_bias[bs][et] = P.bias ? __bfloat162float(P.bias[nb * kGemmBN + et]) : 0.0f;
+        s_bias[bs][kGemmBN + et] = P.bias ? __bfloat162float(P.bias[P.n + nb * kGemmBN + et]) : 0.0f;
+        named_bar_sync(1, 128);
+      }
       mbar_wait(&bars.acc_full[ab], ause & 1);
       tc_fence_after();
       const uint32_t acc = tmem + ab * (2 * kGemmBN) + lane_off;
@@ -180,14 +264,15 @@ gemm_geglu_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         uint32_t pk[16];
 #pragma unroll
         for (int i = 0; i < 32; i += 4) {
-          const float4 bv = *reinterpret_cast<const float4*>(&s_bias[ab][c * 32 + i]);            // broadcast reads
-          const float4 bg = *reinterpret_cast<const float4*>(&s_bias[ab][kGemmBN + c * 32 + i]);
-          const float v0 = __uint_as_float(v[i]) + bv.x, v1 = __uint_as_float(v[i + 1]) + bv.y;
-          const float v2 = __uint_as_float(v[i + 2]) + bv.z, v3 = __uint_as_float(v[i + 3]) + bv.w;
-          const float g0 = __uint_as_float(g[i]) + bg.x, g1 = __uint_as_float(g[i + 1]) + bg.y;
-          const float g2 = __uint_as_float(g[i + 2]) + bg.z, g3 = __uint_as_float(g[i + 3]) + bg.w;
-          pk[i / 2] = pack_bf16(v0 * gelu_as(g0), v1 * gelu_as(g1));
-          pk[i / 2 + 1] = pack_bf16(v2 * gelu_as(g2), v3 * gelu_as(g3));
+          const float4 bv = *reinterpret_cast<const float4*>(&s_bias[bs][c * 32 + i]);            // broadcast reads
+          const float4 bg = *reinterpret_cast<const float4*>(&s_bias[bs][kGemmBN + c * 32 + i]);
+          const float2 va = __fadd2_rn(make_float2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])), make_float2(bv.x, bv.y));
+          const float2 vb = __fadd2_rn(make_float2(__uint_as_float(v[i + 2]), __uint_as_float(v[i + 3])), make_float2(bv.z, bv.w));
+          const float2 ga = __fadd2_rn(make_float2(__uint_as_float(g[i]), __uint_as_float(g[i + 1])), make_float2(bg.x, bg.y));
+          const float2 gb = __fadd2_rn(make_float2(__uint_as_float(g[i + 2]), __uint_as_float(g[i + 3])), make_float2(bg.z, bg.w));
+          const float2 oa = geglu_pair(va, ga), ob = geglu_pair(vb, gb);
+          pk[i / 2] = pack_bf16(oa.x, oa.y);
+          pk[i / 2 + 1] = pack_bf16(ob.x, ob.y);
         }
         if (row < P.rows) {
 #pragma unroll
@@ -263,14 +348,30 @@ extern "C" int vf_linear_geglu(const void* x, const void* w, const void* bias, v
   P.m_blocks = (int)((rows + kGemmBM - 1) / kGemmBM);
   P.n_blocks = n / kGemmBN;
   P.k_blocks = (k + kGemmBK - 1) / kGemmBK;
-  const size_t smem = 1024 + (size_t)kGemmStages * kStageBytes;
+  static int w_res_knob = -1;      // VF_GEMM_WRES=0 forces the streaming kernel
+  if (w_res_knob < 0) { const char* e = getenv("VF_GEMM_WRES"); w_res_knob = e ? atoi(e) : 1; }
+  constexpr size_t kTail = 128 + 2 * 2 * kGemmBN * sizeof(float);      // barriers + bias
+  static_assert(sizeof(GemmBarriers) <= 128, "barrier block");
+  const size_t smem_res = 1008 + (size_t)P.k_blocks * kBTileBytes + (size_t)kGemmStages * kATileBytes + 128 + 2 * kGemmBN * sizeof(float);
+  const bool resident = w_res_knob && smem_res <= 232448 && P.n_blocks <= num_sms() && P.m_blocks >= 4 * (num_sms() / P.n_blocks);
+  if (resident) {
+    static size_t attr_r = 0;
+    if (smem_res > attr_r) {
+      VF_CUDA_TRY(cudaFuncSetAttribute(gemm_geglu_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_res));
+      attr_r = smem_res;
+    }
+    const int groups = num_sms() / P.n_blocks;
+    gemm_geglu_kernel<true><<<groups * P.n_blocks, kGemmThreads, smem_res, (cudaStream_t)stream>>>(ma, mw, P);
+    return check_cuda(cudaGetLastError(), "gemm_geglu_kernel<resident W> launch");
+  }
+  const size_t smem = 1008 + (size_t)kGemmStages * kStageBytes + kTail;
   static bool attr = false;
   if (!attr) {
-    VF_CUDA_TRY(cudaFuncSetAttribute(gemm_geglu_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    VF_CUDA_TRY(cudaFuncSetAttribute(gemm_geglu_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = true;
   }
   long long grid = (long long)P.m_blocks * P.n_blocks;
   if (grid > num_sms()) grid = num_sms();
-  gemm_geglu_kernel<<<(int)grid, kGemmThreads, smem, (cudaStream_t)stream>>>(ma, mw, P);
+  gemm_geglu_kernel<false><<<(int)grid, kGemmThreads, smem, (cudaStream_t)stream>>>(ma, mw, P);
   return check_cuda(cudaGetLastError(), "gemm_geglu_kernel launch");
 }
