@@ -21,6 +21,7 @@ def main():
     ap.add_argument("--frames", type=int, default=32)
     ap.add_argument("--top", type=int, default=45)
     ap.add_argument("--elide-recon", action="store_true")
+    ap.add_argument("--shapes", default="", help="comma list of aten op names to break down by input shape (e.g. aten::add,aten::copy_)")
     a = ap.parse_args()
     from vface_b200.ldm.models.diffusion.ddim_w_inv import DDIMSampler
     device = torch.device("cuda:0")
@@ -50,11 +51,17 @@ def main():
             x = one(i, x)
         torch.cuda.synchronize()
         from torch.profiler import ProfilerActivity, profile
-        with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
+        with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA], record_shapes=bool(a.shapes)) as prof:
             for i in range(3, 5):
                 x = one(i, x)
             torch.cuda.synchronize()
     print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=a.top, max_name_column_width=90))
+    if a.shapes:
+        want = set(a.shapes.split(","))
+        rows = [e for e in prof.key_averages(group_by_input_shape=True) if e.key in want]
+        rows.sort(key=lambda e: -e.device_time_total)
+        for e in rows[:40]:
+            print(f"{e.key:18s} calls={e.count:4d} cuda_total={e.device_time_total / 1e3:8.3f} ms  shapes={e.input_shapes}")
 
 
 if __name__ == "__main__":

@@ -28,7 +28,7 @@ extern "C" {
 #define VF_F32 0
 #define VF_BF16 1
 
-#define VF_ABI_VERSION 4
+#define VF_ABI_VERSION 5
 
 /* ABI version of the loaded library (== VF_ABI_VERSION). */
 int vf_abi_version(void);
@@ -186,6 +186,13 @@ int vf_linear_geglu(const void* x, const void* w, const void* bias, void* out,
  */
 int vf_add_bias(const void* a, const void* b, const void* bias, long long rows_per_bias, void* out,
                 long long rows, int c, int dtype, void* stream);
+
+/*
+ * Nearest-neighbour 2x upsampling of a channels-last map x: (n, h, w, c) -> out: (n, 2h, 2w, c).
+ * Replaces F.interpolate(x, scale_factor=2, mode="nearest") in Upsample.forward
+ * (ldm/modules/diffusionmodules/openaimodel.py:107-117; also model.py:52-56 of the first-stage decoder).
+ */
+int vf_upsample_nearest2x_nhwc(const void* x, void* out, int n, int h, int w, int c, int dtype, void* stream);
 
 #ifdef __cplusplus
 }

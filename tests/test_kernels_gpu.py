@@ -368,3 +368,13 @@ def test_linear_geglu_matches_unfused_module_path():
     # the unfused path rounds the projection to bf16 before gating; the fused one gates the fp32 accumulator
     assert (fused.float() - plain.float()).abs().max().item() < 4e-2
     assert ((fused.float() - plain.float()).norm() / plain.float().norm()).item() < 5e-3
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_upsample_nearest2x_matches_interpolate(dtype):
+    from vface_b200 import ops
+    x = torch.randn(3, 64, 5, 7, device=_dev()).to(dtype).contiguous(memory_format=torch.channels_last)
+    got = ops.upsample_nearest2x(x)
+    want = torch.nn.functional.interpolate(x, scale_factor=2, mode="nearest")
+    assert got.shape == want.shape and torch.equal(got, want)
+    assert got.is_contiguous(memory_format=torch.channels_last)

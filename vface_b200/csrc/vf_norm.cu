@@ -688,6 +688,32 @@ add_bias_kernel(const T* __restrict__ a, const T* __restrict__ b, const T* __res
   }
 }
 
+// nearest-neighbour 2x upsampling of a channels-last map: out[n, 2y+a, 2x+b, :] = in[n, y, x, :].
+// (ATen's upsample_nearest2d NHWC kernel moves one element per thread: 0.8 ms for the 32x32x640 -> 64x64 level
+// of a 96-sample batch, 8x the time the 0.63 GB of traffic needs.)  One thread = one 16-byte chunk of an INPUT
+// pixel, stored four times.
+template <typename T>
+__global__ void __launch_bounds__(256)
+upsample2x_kernel(const T* __restrict__ in, T* __restrict__ out, long long n_pix, int h, int w, int chunks) {
+  constexpr int E = V16<T>::E;
+  const long long total = n_pix * chunks;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long pix = i / chunks;
+    const int ch = (int)(i - pix * chunks) * E;
+    const int x = (int)(pix % w);
+    const long long t = pix / w;
+    const int y = (int)(t % h);
+    const long long n = t / h;
+    const uint4 v = ld_nc_v4(in + pix * (long long)chunks * E + ch);
+    T* o = out + (((n * 2 * h + 2 * y) * 2 * w) + 2 * x) * (long long)chunks * E + ch;
+    const long long row = 2LL * w * chunks * E;
+    st_na_v4(o, v);
+    st_na_v4(o + (long long)chunks * E, v);
+    st_na_v4(o + row, v);
+    st_na_v4(o + row + (long long)chunks * E, v);
+  }
+}
+
 static int ew_grid(long long total) {
   long long blocks = (total + 255) / 256;
   const long long cap = (long long)num_sms() * 16;
@@ -864,4 +890,20 @@ extern "C" int vf_add_bias(const void* a, const void* b, const void* bias, long 
     add_bias_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)a, (const __nv_bfloat16*)b, (const __nv_bfloat16*)bias,
                                                           (__nv_bfloat16*)out, rows, c, rows_per_bias);
   return check_cuda(cudaGetLastError(), "add_bias_kernel launch");
+}
+
+extern "C" int vf_upsample_nearest2x_nhwc(const void* x, void* out, int n, int h, int w, int c, int dtype, void* stream) {
+  using namespace vf;
+  if (int rc = check_device()) return rc;
+  if (!x || !out) return fail("vf_upsample_nearest2x_nhwc: null pointer");
+  if (dtype != VF_F32 && dtype != VF_BF16) return fail("vf_upsample_nearest2x_nhwc: bad dtype %d", dtype);
+  const int e = dtype == VF_F32 ? 4 : 8;
+  if (n <= 0 || h <= 0 || w <= 0 || c <= 0 || c % e) return fail("vf_upsample_nearest2x_nhwc: bad shape n=%d h=%d w=%d c=%d", n, h, w, c);
+  if (!al16(x) || !al16(out)) return fail("vf_upsample_nearest2x_nhwc: pointers must be 16-byte aligned");
+  const long long n_pix = (long long)n * h * w;
+  const int grid = ew_grid(n_pix * (c / e));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == VF_F32) upsample2x_kernel<float><<<grid, 256, 0, st>>>((const float*)x, (float*)out, n_pix, h, w, c / e);
+  else upsample2x_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)out, n_pix, h, w, c / e);
+  return check_cuda(cudaGetLastError(), "upsample2x_kernel launch");
 }

@@ -44,7 +44,7 @@ class Upsample(nn.Module):
             self.conv = nn.Conv2d(in_channels, in_channels, kernel_size=3, stride=1, padding=1)
 
     def forward(self, x):
-        x = F.interpolate(x, scale_factor=2.0, mode="nearest")
+        x = ops.upsample_nearest2x(x)                    # F.interpolate(scale_factor=2.0, mode="nearest"), channels-last
         return self.conv(x) if self.with_conv else x
 
 

@@ -38,6 +38,8 @@ class TimestepEmbedSequential(nn.Sequential, TimestepBlock):
                 x = layer(x, emb)
             elif isinstance(layer, SpatialTransformer):
                 x = layer(x, context)
+            elif isinstance(layer, nn.Conv2d):
+                x = ops.conv2d_nhwc(x, layer)
             else:
                 x = layer(x)
         return x
@@ -54,8 +56,8 @@ class Upsample(nn.Module):
             self.conv = nn.Conv2d(self.channels, self.out_channels, 3, padding=padding)
 
     def forward(self, x):
-        x = F.interpolate(x, scale_factor=2, mode="nearest")
-        return self.conv(x) if self.use_conv else x
+        x = ops.upsample_nearest2x(x)                    # F.interpolate(scale_factor=2, mode="nearest"), channels-last
+        return ops.conv2d_nhwc(x, self.conv) if self.use_conv else x
 
 
 class Downsample(nn.Module):
@@ -71,7 +73,7 @@ class Downsample(nn.Module):
             self.op = nn.AvgPool2d(kernel_size=2, stride=2)
 
     def forward(self, x):
-        return self.op(x)
+        return ops.conv2d_nhwc(x, self.op) if self.use_conv else self.op(x)
 
 
 class ResBlock(TimestepBlock):
@@ -278,5 +280,5 @@ class UNetModel(nn.Module):
                 features.append(h)
         gn = self.out[0]
         ht = ops.group_norm_nhwc(h.permute(0, 2, 3, 1).contiguous(), gn.weight, gn.bias, gn.eps, gn.num_groups, silu=True)
-        out = self.out[2](ht.permute(0, 3, 1, 2)).to(x.dtype).contiguous()
+        out = ops.conv2d_nhwc(ht.permute(0, 3, 1, 2), self.out[2]).to(x.dtype).contiguous()
         return (out, features) if return_features else out
