@@ -134,6 +134,15 @@ def local_clip(frames, rank, steps):
     return clip
 
 
+def workload_config(frames, world, n_branches=3):
+    """The `config` object of the JSON line -- identical for the vface_b200 arm and the reference arm."""
+    return dict(workload="VFace full pipeline, 32-frame 512x512 clip per GPU, DDIM-50 with CFG 3.0, bf16",
+                frames_per_gpu=frames, total_frames=frames * world, ddim_steps=DDIM_STEPS, cfg_scale=CFG_SCALE,
+                unet_batch_per_step=n_branches * frames, branches=n_branches, parallelism=f"frame-shard x{world}",
+                l2="step working set (1.7 GB weights + activations) far exceeds the 126 MB L2; no flush needed",
+                weights="random-init REFace UNet 859.5M params, zero-modules re-randomised (seed 1)")
+
+
 # ---- CPU baseline (oracle port) -------------------------------------------------------------------------------
 def cpu_step_seconds(sd, frames, warm, reps):
     """Seconds per denoising step of the reference path on the host cores (oracle port), `frames` frames."""
@@ -192,9 +201,7 @@ def run_reference_arm(args, rank):
     line = dict(impl="reference", metric=METRIC, value=value, unit=UNIT, n_gpus=args.gpus, steps=K, warmup=W,
                 ms_per_step=t_step * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
                 data="synthetic",
-                config=dict(workload="VFace full pipeline, 32-frame 512x512 clip per GPU, DDIM-50, CFG 3.0 "
-                                     "(reference CPU path measured on a bounded 1-frame sample)",
-                            frames_per_step=frames, ddim_steps=DDIM_STEPS, cfg_scale=CFG_SCALE),
+                config=workload_config(args.frames, max(args.gpus, 1)),
                 cpu_baseline=dict(value=value, unit=UNIT, cores=cores, kind="port", sample=sample),
                 e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     if note:
@@ -370,11 +377,7 @@ def main():
     if rank == 0:
         line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=K, warmup=W, ms_per_step=ms_per_step,
                     higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16", data="synthetic",
-                    config=dict(workload="VFace full pipeline, 32-frame 512x512 clip per GPU, DDIM-50 with CFG 3.0, bf16",
-                                frames_per_gpu=frames, total_frames=total_frames, ddim_steps=DDIM_STEPS, cfg_scale=CFG_SCALE,
-                                unet_batch_per_step=n_branches * frames, branches=n_branches, parallelism=f"frame-shard x{world}",
-                                l2="step working set (1.7 GB weights + activations) far exceeds the 126 MB L2; no flush needed",
-                                weights="random-init REFace UNet 859.5M params, zero-modules re-randomised (seed 1)"),
+                    config=workload_config(frames, world, n_branches),
                     clocks=clock_info, e2e=e2e, gpu_launches=int(lsum.item()), roofline=roof, cpu_baseline=cpu,
                     halo=dict(messages=shard.halo_messages, bytes=shard.halo_bytes) if world > 1 else None)
         print(json.dumps(line), flush=True)

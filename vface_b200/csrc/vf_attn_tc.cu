@@ -70,11 +70,18 @@ template <int kRegs> __device__ __forceinline__ void reg_inc() { asm volatile("s
 // as the softmax threads have loaded it into registers (s_free), so QK_{j+1} is issued while softmax_j is
 // still in its exponentials and the softmax warps never wait for the tensor pipe; PV_j follows when P_j is
 // complete (p_full) and releases P with its own commit (p_empty).  160 TMEM columns -> three CTAs per SM.
-template <int BN, int kTmemCols, int kMinBlocks, int kEmu, bool kSplitP, int kStages>
+template <int BN, int kTmemCols, int kMinBlocks, int kEmu, int kPMode, int kStages>
 __global__ void __launch_bounds__(kTcThreads, kMinBlocks)
 attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                const __grid_constant__ CUtensorMap map_v, const __grid_constant__ CUtensorMap map_k2,
                const __grid_constant__ CUtensorMap map_v2, const AttnTcParams P) {
+  // kPMode: 0 = P aliases S (128 columns, 4 CTAs/SM, QK_{j+1} behind PV_j);
+  //         1 = P in its own BN/2-column allocation (BN = 64: 128 + 32 columns, 3 CTAs/SM);
+  //         2 = P inside the main allocation behind O (BN = 48, d_pad <= 48: S 48 | O 48 | P 24 = 120 of 128
+  //             columns, 4 CTAs/SM with the early QK_{j+1} of mode 1).
+  constexpr bool kSplitP = kPMode != 0;
+  static_assert(BN % 16 == 0 && (BN == 64 || BN == 48), "key tile of 48 or 64 rows");
+  static_assert(kPMode != 2 || BN + 48 + BN / 2 <= kTmemCols, "S | O | P must fit the allocation");
   extern __shared__ unsigned char smem_dyn[];
   __shared__ TcBarriers bars;
 
@@ -116,7 +123,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     fence_barrier_init();
   }
   if (warp == 1) {
-    if (kSplitP) {
+    if (kPMode == 1) {
       tmem_alloc_only<kTmemCols>(&bars.tmem_base);
       tmem_alloc_only<BN / 2>(&bars.tmem_base_p);
       tmem_relinquish();
@@ -129,7 +136,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
   tc_fence_after();
   const uint32_t tmem = bars.tmem_base;
   const uint32_t tm_s = tmem;          // S (fp32, BN columns); P (bf16x2) overwrites its first BN/2 columns
-  const uint32_t tm_p = kSplitP ? bars.tmem_base_p : tmem;
+  const uint32_t tm_p = kPMode == 1 ? bars.tmem_base_p : kPMode == 2 ? tmem + BN + 48 : tmem;
   const uint32_t tm_o = tmem + BN;
 
   if (warp < 4) {
@@ -234,9 +241,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
       if (P.spin) mbar_wait_spin(&bars.s_full, (uint32_t)j & 1);
       else mbar_wait(&bars.s_full, (uint32_t)j & 1);
       tc_fence_after();
-      uint32_t sr[BN / 32][32];
-#pragma unroll
-      for (int c = 0; c < BN / 32; ++c) tmem_ld_x32(tm_s + lane_off + c * 32, sr[c]);
+      uint32_t sr[BN];
+      tmem_ld_x32(tm_s + lane_off, *reinterpret_cast<uint32_t(*)[32]>(&sr[0]));
+      if (BN == 64) tmem_ld_x32(tm_s + lane_off + 32, *reinterpret_cast<uint32_t(*)[32]>(&sr[32]));
+      else tmem_ld_x16(tm_s + lane_off + 32, &sr[32]);
       if (kSplitP && j > 0) {
         // P_{j-1} hand-over, deferred to here so that its TMEM-store latency overlaps this tile's S load
         tmem_wait_st();
@@ -253,22 +261,18 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
 
       if (valid < BN) {
 #pragma unroll
-        for (int c = 0; c < BN / 32; ++c)
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (c * 32 + i >= valid) sr[c][i] = 0xff800000u;   // -inf
+        for (int i = 0; i < BN; ++i)
+          if (i >= valid) sr[i] = 0xff800000u;   // -inf
       }
       // row max: 3-input FMNMX3 in four independent chains
       float mx[4];
 #pragma unroll
-      for (int t = 0; t < 4; ++t) mx[t] = __uint_as_float(sr[0][t]);
+      for (int t = 0; t < 4; ++t) mx[t] = __uint_as_float(sr[t]);
 #pragma unroll
-      for (int c = 0; c < BN / 32; ++c)
+      for (int i = 0; i < BN; i += 8)
 #pragma unroll
-        for (int i = 0; i < 32; i += 8)
-#pragma unroll
-          for (int t = 0; t < 4; ++t)
-            mx[t] = fmax3(mx[t], __uint_as_float(sr[c][i + 2 * t]), __uint_as_float(sr[c][i + 2 * t + 1]));
+        for (int t = 0; t < 4; ++t)
+          mx[t] = fmax3(mx[t], __uint_as_float(sr[i + 2 * t]), __uint_as_float(sr[i + 2 * t + 1]));
       const float cand = fmaxf(fmax3(mx[0], mx[1], mx[2]), mx[3]) * P.scale_log2;
       float alpha = 1.0f;
       bool need = false;
@@ -284,42 +288,41 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
       const uint64_t c2 = pack2(P.scale_log2, P.scale_log2);
       const uint64_t nm2 = pack2(-m_ref, -m_ref);
       uint64_t acc_a = 0ull, acc_b = 0ull;     // (+0.0f, +0.0f)
+      uint32_t pk[BN / 2];
 #pragma unroll
-      for (int g = 0; g < BN / 64; ++g) {            // 64 score columns -> 32 packed bf16x2 columns
-        uint32_t pk[32];
-#pragma unroll
-        for (int cc = 0; cc < 2; ++cc)
-#pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            const int c = g * 2 + cc;
-            const uint64_t xa = ffma2(pack2(__uint_as_float(sr[c][i + 0]), __uint_as_float(sr[c][i + 1])), c2, nm2);
-            const uint64_t xb = ffma2(pack2(__uint_as_float(sr[c][i + 2]), __uint_as_float(sr[c][i + 3])), c2, nm2);
-            float p0, p1, p2, p3;
-            if (((i / 2) & 3) < kEmu) {
-              exp2_poly2(xa, p0, p1);
-            } else {
-              float t0, t1;
-              unpack2(xa, t0, t1);
-              p0 = ex2_approx(t0); p1 = ex2_approx(t1);
-            }
-            if (((i / 2 + 1) & 3) < kEmu) {
-              exp2_poly2(xb, p2, p3);
-            } else {
-              float t2, t3;
-              unpack2(xb, t2, t3);
-              p2 = ex2_approx(t2); p3 = ex2_approx(t3);
-            }
-            acc_a = fadd2(acc_a, pack2(p0, p1));
-            acc_b = fadd2(acc_b, pack2(p2, p3));
-            pk[cc * 16 + i / 2 + 0] = pack_bf16(p0, p1);
-            pk[cc * 16 + i / 2 + 1] = pack_bf16(p2, p3);
-          }
-        if (kSplitP && g == 0 && j > 0) {              // PV_{j-1} still reads P (and writes O) until its commit
-          if (P.spin) mbar_wait_spin(&bars.p_empty, (uint32_t)(j - 1) & 1);
-          else mbar_wait(&bars.p_empty, (uint32_t)(j - 1) & 1);
-          tc_fence_after();
+      for (int i = 0; i < BN; i += 4) {
+        const uint64_t xa = ffma2(pack2(__uint_as_float(sr[i + 0]), __uint_as_float(sr[i + 1])), c2, nm2);
+        const uint64_t xb = ffma2(pack2(__uint_as_float(sr[i + 2]), __uint_as_float(sr[i + 3])), c2, nm2);
+        float p0, p1, p2, p3;
+        if (((i / 2) & 3) < kEmu) {
+          exp2_poly2(xa, p0, p1);
+        } else {
+          float t0, t1;
+          unpack2(xa, t0, t1);
+          p0 = ex2_approx(t0); p1 = ex2_approx(t1);
         }
-        tmem_st_x32(tm_p + lane_off + g * 32, pk);
+        if (((i / 2 + 1) & 3) < kEmu) {
+          exp2_poly2(xb, p2, p3);
+        } else {
+          float t2, t3;
+          unpack2(xb, t2, t3);
+          p2 = ex2_approx(t2); p3 = ex2_approx(t3);
+        }
+        acc_a = fadd2(acc_a, pack2(p0, p1));
+        acc_b = fadd2(acc_b, pack2(p2, p3));
+        pk[i / 2 + 0] = pack_bf16(p0, p1);
+        pk[i / 2 + 1] = pack_bf16(p2, p3);
+      }
+      if (kSplitP && j > 0) {              // PV_{j-1} still reads P (and writes O) until its commit
+        if (P.spin) mbar_wait_spin(&bars.p_empty, (uint32_t)(j - 1) & 1);
+        else mbar_wait(&bars.p_empty, (uint32_t)(j - 1) & 1);
+        tc_fence_after();
+      }
+      if (BN == 64) {
+        tmem_st_x32(tm_p + lane_off, *reinterpret_cast<const uint32_t(*)[32]>(&pk[0]));
+      } else {
+        tmem_st_x16(tm_p + lane_off, &pk[0]);
+        tmem_st_x8(tm_p + lane_off + 16, *reinterpret_cast<const uint32_t(*)[8]>(&pk[16]));
       }
       float sa0, sa1, sb0, sb1;
       unpack2(acc_a, sa0, sa1);
@@ -368,7 +371,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc<kTmemCols>(tmem);
-    if (kSplitP) tmem_dealloc<BN / 2>(bars.tmem_base_p);
+    if (kPMode == 1) tmem_dealloc<BN / 2>(bars.tmem_base_p);
   }
 }
 
@@ -404,17 +407,17 @@ static int make_map(CUtensorMap* m, const void* base, int batch, int heads, int 
   return 0;
 }
 
-template <int BN, int kTmemCols, int kMinBlocks, int kEmu, bool kSplitP = false, int kStages = 2>
+template <int BN, int kTmemCols, int kMinBlocks, int kEmu, int kPMode = 0, int kStages = 2>
 static int launch_tc(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const CUtensorMap& mk2,
                      const CUtensorMap& mv2, const AttnTcParams& P, int batch, cudaStream_t st) {
   const size_t smem = 1024 + (size_t)P.kb * (kBM * 128 + 2 * kStages * BN * 128);
   static bool attr = false;
   if (!attr) {
-    VF_CUDA_TRY(cudaFuncSetAttribute(attn_tc_kernel<BN, kTmemCols, kMinBlocks, kEmu, kSplitP, kStages>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    VF_CUDA_TRY(cudaFuncSetAttribute(attn_tc_kernel<BN, kTmemCols, kMinBlocks, kEmu, kPMode, kStages>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr = true;
   }
   dim3 grid((P.n_q + kBM - 1) / kBM, batch * P.heads);
-  attn_tc_kernel<BN, kTmemCols, kMinBlocks, kEmu, kSplitP, kStages><<<grid, kTcThreads, smem, st>>>(mq, mk, mv, mk2, mv2, P);
+  attn_tc_kernel<BN, kTmemCols, kMinBlocks, kEmu, kPMode, kStages><<<grid, kTcThreads, smem, st>>>(mq, mk, mv, mk2, mv2, P);
   return check_cuda(cudaGetLastError(), "attn_tc_kernel launch");
 }
 
@@ -447,7 +450,22 @@ int launch_attn_tc(const void* q, const void* k, const void* v, void* o, int bat
     if (spin < 0) { const char* e = getenv("VF_ATTN_SPIN"); spin = e ? atoi(e) : 0; }
     P.spin = spin;
   }
-  const int bn = 64;
+  static int emu = -1;      // tuning knob: VF_ATTN_EMU = 0..3 pairs of every 4 on the FMA pipe
+  if (emu < 0) {
+    const char* e = getenv("VF_ATTN_EMU");
+    emu = e ? atoi(e) : 0;
+    if (emu < 0 || emu > 3) emu = 0;
+  }
+  // VF_ATTN_SPLITP: 1 (default) P in its own TMEM allocation, key tiles of 64, 3 CTAs/SM; 3 = key tiles of 48 with
+  // P behind O in one 128-column allocation, 4 CTAs/SM (d_pad <= 48); 0 = aliased P, 4 CTAs/SM; 2 = mode 1 with a
+  // 3-stage K/V ring.
+  static int split = -1;
+  if (split < 0) {
+    const char* e = getenv("VF_ATTN_SPLITP");
+    split = e ? atoi(e) : 1;
+  }
+  const bool bn48 = split == 3 && P.d_pad <= 48;
+  const int bn = bn48 ? 48 : 64;
   CUtensorMap mq, mk, mv, mk2, mv2;
   if (int rc = make_map(&mq, q, batch, heads, n_q, d, ld_q, kBM)) return rc;
   if (int rc = make_map(&mk, k, batch, heads, n_kv, d, ld_k, bn)) return rc;
@@ -459,24 +477,18 @@ int launch_attn_tc(const void* q, const void* k, const void* v, void* o, int bat
     mk2 = mk;
     mv2 = mv;
   }
-  // TMEM: BN S columns (P aliased) + d_pad O columns, rounded up to a power of two.
-  static int emu = -1;      // tuning knob: VF_ATTN_EMU = 0..3 pairs of every 4 on the FMA pipe
-  if (emu < 0) {
-    const char* e = getenv("VF_ATTN_EMU");
-    emu = e ? atoi(e) : 0;
-    if (emu < 0 || emu > 3) emu = 0;
+  if (bn48) {
+    switch (emu) {
+      case 1: return launch_tc<48, 128, 4, 1, 2>(mq, mk, mv, mk2, mv2, P, batch, st);
+      default: return launch_tc<48, 128, 4, 0, 2>(mq, mk, mv, mk2, mv2, P, batch, st);
+    }
   }
-  static int split = -1;    // default: P in its own TMEM allocation, 3 CTAs / SM (see kernel comment); VF_ATTN_SPLITP=0: aliased P, 4 CTAs / SM
-  if (split < 0) {
-    const char* e = getenv("VF_ATTN_SPLITP");
-    split = e ? atoi(e) : 1;
-  }
-  if (P.d_pad <= 64 && split == 2) return launch_tc<64, 128, 3, 0, true, 3>(mq, mk, mv, mk2, mv2, P, batch, st);   // 3-stage K/V ring
+  if (P.d_pad <= 64 && split == 2) return launch_tc<64, 128, 3, 0, 1, 3>(mq, mk, mv, mk2, mv2, P, batch, st);   // 3-stage K/V ring
   if (P.d_pad <= 64 && split) {
     switch (emu) {
-      case 1: return launch_tc<64, 128, 3, 1, true>(mq, mk, mv, mk2, mv2, P, batch, st);
-      case 2: return launch_tc<64, 128, 3, 2, true>(mq, mk, mv, mk2, mv2, P, batch, st);
-      default: return launch_tc<64, 128, 3, 0, true>(mq, mk, mv, mk2, mv2, P, batch, st);
+      case 1: return launch_tc<64, 128, 3, 1, 1>(mq, mk, mv, mk2, mv2, P, batch, st);
+      case 2: return launch_tc<64, 128, 3, 2, 1>(mq, mk, mv, mk2, mv2, P, batch, st);
+      default: return launch_tc<64, 128, 3, 0, 1>(mq, mk, mv, mk2, mv2, P, batch, st);
     }
   }
   if (P.d_pad <= 64) {                                                                   // 48 KB smem: 4 CTAs / SM
