@@ -81,7 +81,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
   //             columns, 4 CTAs/SM with the early QK_{j+1} of mode 1).
   constexpr bool kSplitP = kPMode != 0;
   static_assert(BN % 16 == 0 && (BN == 64 || BN == 48), "key tile of 48 or 64 rows");
-  static_assert(kPMode != 2 || BN + 48 + BN / 2 <= kTmemCols, "S | O | P must fit the allocation");
+  constexpr int kOCols = kTmemCols == 128 ? 48 : 160;      // O columns reserved in front of P (mode 2)
+  static_assert(kPMode != 2 || BN + kOCols + BN / 2 <= kTmemCols, "S | O | P must fit the allocation");
   extern __shared__ unsigned char smem_dyn[];
   __shared__ TcBarriers bars;
 
@@ -136,7 +137,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
   tc_fence_after();
   const uint32_t tmem = bars.tmem_base;
   const uint32_t tm_s = tmem;          // S (fp32, BN columns); P (bf16x2) overwrites its first BN/2 columns
-  const uint32_t tm_p = kPMode == 1 ? bars.tmem_base_p : kPMode == 2 ? tmem + BN + 48 : tmem;
+  const uint32_t tm_p = kPMode == 1 ? bars.tmem_base_p : kPMode == 2 ? tmem + BN + kOCols : tmem;
   const uint32_t tm_o = tmem + BN;
 
   if (warp < 4) {
@@ -500,7 +501,10 @@ int launch_attn_tc(const void* q, const void* k, const void* v, void* o, int bat
       default: return launch_tc<64, 128, 4, 0>(mq, mk, mv, mk2, mv2, P, batch, st);
     }
   }
-  return launch_tc<64, 256, 2, 0>(mq, mk, mv, mk2, mv2, P, batch, st);                    // d in (64, 192]
+  // d in (64, 192]: 256 TMEM columns, two CTAs/SM.  Up to d = 160 (the UNet's 80 and 160) P sits behind O in
+  // the same allocation (S 64 | O 160 | P 32) so QK_{j+1} is issued early as in the d <= 64 kernel.
+  if (split && P.d_pad <= 160) return launch_tc<64, 256, 2, 0, 2>(mq, mk, mv, mk2, mv2, P, batch, st);
+  return launch_tc<64, 256, 2, 0>(mq, mk, mv, mk2, mv2, P, batch, st);
 }
 
 }  // namespace vf
