@@ -6,12 +6,13 @@
 //
 // Design (sm_100a):
 //   * one CTA = one 128-row query tile of one (batch, head); 8 warps in two warpgroups:
-//       warpgroup 0  warp 0 = TMA producer (cp.async.bulk.tensor 4-D boxes, 128B swizzle, zero fill of
+//       warpgroup 0  (warps 0-3) softmax / correction / epilogue, one thread per query row (TMEM lane),
+//                    with the registers of warpgroup 1 added (setmaxnreg.inc)
+//       warpgroup 1  warp 4 = TMA producer (cp.async.bulk.tensor 4-D boxes, 128B swizzle, zero fill of
 //                             the head-dim padding d -> 64k and of ragged row tails),
-//                    warp 1 = tcgen05.mma issuer + TMEM allocator (one elected lane issues),
-//                    warps 2,3 idle; the group gives its registers away (setmaxnreg.dec)
-//       warpgroup 1  softmax / correction / epilogue, one thread per query row (TMEM lane),
-//                    with the registers of warpgroup 0 added (setmaxnreg.inc)
+//                    warp 7 = tcgen05.mma issuer + TMEM allocator -- the highest warp id, so the scheduler
+//                             serves it first (one elected lane issues, the loop is warp-uniform),
+//                    warps 5,6 idle; the group gives its registers away (setmaxnreg.dec)
 //   * S = Q K^T      : tcgen05.mma  SS, M=128, N=BN, K=16 x ceil(d/16), fp32 accumulator in TMEM
 //   * P (bf16)       : written back over the first BN/2 columns of S by the softmax threads
 //                      (tcgen05.st) once S is in registers -- never to smem/HBM
@@ -38,6 +39,8 @@ namespace vf {
 using namespace sm100;
 
 constexpr int kTcThreads = 256;
+constexpr int kTmaWarp = 4;         // warps 0..3: softmax (one per TMEM lane quarter); 4: TMA producer; 7: MMA issuer
+constexpr int kMmaWarp = 7;
 constexpr int kBM = 128;            // query rows per CTA
 constexpr float kRescaleThreshold = 8.0f;   // log2 units
 
@@ -50,6 +53,17 @@ struct AttnTcParams {
 };
 
 constexpr int kMaxStages = 4;
+
+// Optional phase timing of the softmax warps (build with -DVF_ATTN_TRACE; never in the product build):
+// per-phase clock64 totals of warp 4 of every CTA, summed into g_attn_trace and read with vf_attn_trace_read.
+#ifdef VF_ATTN_TRACE
+__device__ unsigned long long g_attn_trace[16];
+#define VF_TR_DECL unsigned long long tr_t = clock64(), tr_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}
+#define VF_TR(i) do { const unsigned long long n_ = clock64(); tr_acc[i] += n_ - tr_t; tr_t = n_; } while (0)
+#else
+#define VF_TR_DECL
+#define VF_TR(i)
+#endif
 
 struct __align__(8) TcBarriers {
   uint64_t q_full;
@@ -123,7 +137,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     mbar_init(&bars.p_empty, 1);
     fence_barrier_init();
   }
-  if (warp == 1) {
+  if (warp == kMmaWarp) {
     if (kPMode == 1) {
       tmem_alloc_only<kTmemCols>(&bars.tmem_base);
       tmem_alloc_only<BN / 2>(&bars.tmem_base_p);
@@ -140,9 +154,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
   const uint32_t tm_p = kPMode == 1 ? bars.tmem_base_p : kPMode == 2 ? tmem + BN + kOCols : tmem;
   const uint32_t tm_o = tmem + BN;
 
-  if (warp < 4) {
+  if (warp >= 4) {
     if (kMinBlocks >= 3) reg_dec<24>();
-    if (warp == 0) {
+    if (warp == kTmaWarp) {
       // =========================== TMA producer ==================================================
       if (lane == 0) {
         tma_prefetch_desc(&map_q);
@@ -168,9 +182,15 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
             tma_load_4d(sV + st * kv_bytes + kb * kv_block_bytes, mv, &bars.v_full[st], kb * 64, h, row0, b);
         }
       }
-    } else if (warp == 1) {
+    } else if (warp == kMmaWarp) {
       // =========================== MMA issuer ====================================================
-      if (lane == 0) {
+      // The issuing warp is the HIGHEST-numbered warp of the CTA (the scheduler arbitrates highest warp id
+      // first): a tile needs seven small MMAs and, measured with clock64, a lowest-priority single thread
+      // that competes with three busy softmax warps for issue slots needed ~200 cycles per tcgen05.mma --
+      // 1330 of the 2120 cycles per tile, which made the ISSUER the bound of the kernel, not MUFU or the tensor
+      // pipe.  The loop is warp-uniform (all lanes wait on the barriers, one elected lane issues), so the
+      // descriptors are computed on the uniform datapath instead of moving through R2UR in front of every MMA.
+      {
         const uint32_t idesc_qk = make_idesc_bf16(kBM, BN, false);
         const uint32_t idesc_pv = make_idesc_bf16(kBM, P.d_pad, true);
         const int k_steps = P.d_pad / 16;
@@ -186,52 +206,65 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
             const uint32_t off_blk = (uint32_t)(s >> 2), off_in = (uint32_t)(s & 3) * 32u;
             const uint64_t da = make_smem_desc_sw128(q_addr + off_blk * q_block_bytes + off_in, 16, 1024);
             const uint64_t db = make_smem_desc_sw128(k_addr + st * kv_bytes + off_blk * kv_block_bytes + off_in, 16, 1024);
-            mma_ss(tm_s, da, db, idesc_qk, s > 0);
+            if (elect_one()) mma_ss(tm_s, da, db, idesc_qk, s > 0);
           }
-          tc_commit(&bars.k_empty[st]);
-          tc_commit(&bars.s_full);
+          if (elect_one()) {
+            tc_commit(&bars.k_empty[st]);
+            tc_commit(&bars.s_full);
+          }
         };
 
         mbar_wait(&bars.q_full, 0);
         issue_qk(0);
+        VF_TR_DECL;
         for (int j = 0; j < n_tiles; ++j) {
           const int st = j % kStages;
           if (kSplitP && j + 1 < n_tiles) {
             if (P.spin & 2) mbar_wait_spin(&bars.s_free, (uint32_t)j & 1);
             else mbar_wait(&bars.s_free, (uint32_t)j & 1);      // S_j is in the softmax threads' registers
             tc_fence_after();
+            VF_TR(0);                     // MMA thread: wait s_free
             issue_qk(j + 1);
+            VF_TR(1);                     // issue QK (incl. k_full wait)
           }
           mbar_wait(&bars.v_full[st], (uint32_t)(j / kStages) & 1);
           if (P.spin & 2) mbar_wait_spin(&bars.p_full, (uint32_t)j & 1);
           else mbar_wait(&bars.p_full, (uint32_t)j & 1);        // P_j in TMEM, O rescaled if needed
           tc_fence_after();
-#pragma unroll 1
+          VF_TR(2);                       // wait v_full + p_full
+#pragma unroll
           for (int s = 0; s < BN / 16; ++s) {
             // B = V tile, MN-major: 64 head-dim elements contiguous (128 B) per key row, 8-row groups
             // 1024 B apart (SBO), further 64-wide head-dim blocks kv_block_bytes apart (LBO).
             const uint64_t db = make_smem_desc_sw128(v_addr + st * kv_bytes + (uint32_t)s * 2048u, kv_block_bytes, 1024);
-            mma_ts(tm_o, tm_p + (uint32_t)s * 8u, db, idesc_pv, (j > 0) || (s > 0));
+            if (elect_one()) mma_ts(tm_o, tm_p + (uint32_t)s * 8u, db, idesc_pv, (j > 0) || (s > 0));
           }
-          tc_commit(&bars.v_empty[st]);
+          if (elect_one()) tc_commit(&bars.v_empty[st]);
           if (kSplitP) {
-            tc_commit(&bars.p_empty);
-            if (j + 1 == n_tiles) tc_commit(&bars.o_done);
+            if (elect_one()) {
+              tc_commit(&bars.p_empty);
+              if (j + 1 == n_tiles) tc_commit(&bars.o_done);
+            }
+            VF_TR(3);                     // issue PV
           } else {
             if (j + 1 < n_tiles) issue_qk(j + 1);          // in order behind PV_j: may overwrite P_j
-            else tc_commit(&bars.o_done);
+            else if (elect_one()) tc_commit(&bars.o_done);
           }
         }
+#ifdef VF_ATTN_TRACE
+        if (lane == 0) for (int i = 0; i < 4; ++i) atomicAdd(&g_attn_trace[10 + i], tr_acc[i]);
+#endif
       }
     }
   } else {
     // =========================== softmax / correction / epilogue ================================
     if (kMinBlocks >= 4) reg_inc<104>();
     else if (kMinBlocks == 3) reg_inc<136>();
-    const int quarter = warp & 3;                        // TMEM lane quarter this warp may touch
+    const int quarter = warp;                            // warps 0..3: TMEM lane quarter this warp may touch
     const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
     const int row = q_tile * kBM + quarter * 32 + lane;  // query row owned by this thread
     float m_ref = 0.0f, l = 0.0f;
+    VF_TR_DECL;
 
     for (int j = 0; j < n_tiles; ++j) {
       const bool seg2 = j >= t1;
@@ -242,6 +275,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
       if (P.spin) mbar_wait_spin(&bars.s_full, (uint32_t)j & 1);
       else mbar_wait(&bars.s_full, (uint32_t)j & 1);
       tc_fence_after();
+      VF_TR(j == 0 ? 0 : 1);            // 0: prologue until S_0, 1: s_full waits
       uint32_t sr[BN];
       tmem_ld_x32(tm_s + lane_off, *reinterpret_cast<uint32_t(*)[32]>(&sr[0]));
       if (BN == 64) tmem_ld_x32(tm_s + lane_off + 32, *reinterpret_cast<uint32_t(*)[32]>(&sr[32]));
@@ -259,6 +293,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars.s_free);
       }
+      VF_TR(2);                         // S load (+ deferred P hand-over)
 
       if (valid < BN) {
 #pragma unroll
@@ -284,6 +319,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         m_ref = cand;
         need = true;
       }
+      VF_TR(3);                         // row max, rescale decision
       // p = exp2(s * c - m_ref): packed FFMA2 for the affine part, MUFU.EX2 per element, packed FADD2
       // row sums in two independent chains, bf16x2 packing for the P operand.
       const uint64_t c2 = pack2(P.scale_log2, P.scale_log2);
@@ -314,11 +350,13 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         pk[i / 2 + 0] = pack_bf16(p0, p1);
         pk[i / 2 + 1] = pack_bf16(p2, p3);
       }
+      VF_TR(4);                         // exponentials
       if (kSplitP && j > 0) {              // PV_{j-1} still reads P (and writes O) until its commit
         if (P.spin) mbar_wait_spin(&bars.p_empty, (uint32_t)(j - 1) & 1);
         else mbar_wait(&bars.p_empty, (uint32_t)(j - 1) & 1);
         tc_fence_after();
       }
+      VF_TR(5);                         // p_empty wait
       if (BN == 64) {
         tmem_st_x32(tm_p + lane_off, *reinterpret_cast<const uint32_t(*)[32]>(&pk[0]));
       } else {
@@ -339,6 +377,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
           tmem_st_x8(tm_o + lane_off + c, o8);
         }
       }
+      VF_TR(6);                         // P store, row sums, rare O rescale
       if (!kSplitP || j + 1 == n_tiles) {
         tmem_wait_st();
         tc_fence_before();
@@ -347,6 +386,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
       }
     }
 
+    VF_TR(6);                           // P store, row sums (tail of the last tile)
     // ---- epilogue: O / l -> bf16 -> global ------------------------------------------------------
     mbar_wait(&bars.o_done, 0);
     tc_fence_after();
@@ -366,10 +406,18 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
       }
     }
     tc_fence_before();
+#ifdef VF_ATTN_TRACE
+    VF_TR(7);                           // epilogue
+    if (warp == 0 && lane == 0) {
+      for (int i = 0; i < 8; ++i) atomicAdd(&g_attn_trace[i], tr_acc[i]);
+      atomicAdd(&g_attn_trace[8], 1ull);
+      atomicAdd(&g_attn_trace[9], (unsigned long long)n_tiles);
+    }
+#endif
   }
 
   __syncthreads();
-  if (warp == 1) {
+  if (warp == kMmaWarp) {
     tc_fence_after();
     tmem_dealloc<kTmemCols>(tmem);
     if (kPMode == 1) tmem_dealloc<BN / 2>(bars.tmem_base_p);
@@ -508,3 +556,14 @@ int launch_attn_tc(const void* q, const void* k, const void* v, void* o, int bat
 }
 
 }  // namespace vf
+
+#ifdef VF_ATTN_TRACE
+extern "C" int vf_attn_trace_read(unsigned long long* out16, int reset) {
+  if (cudaMemcpyFromSymbol(out16, vf::g_attn_trace, sizeof(unsigned long long) * 16) != cudaSuccess) return 1;
+  if (reset) {
+    unsigned long long z[16] = {0};
+    if (cudaMemcpyToSymbol(vf::g_attn_trace, z, sizeof(z)) != cudaSuccess) return 1;
+  }
+  return 0;
+}
+#endif
