@@ -292,6 +292,32 @@ def test_attention_strided_qkv_and_large_logits():
     assert err < BF16_TOL * max(1.0, float(np.abs(want).max()) / 2.0), err
 
 
+@pytest.mark.parametrize("d,heads", [(40, 8), (80, 4)])
+def test_attention_score_jump_takes_exact_path(d, heads):
+    """Rows whose scores jump by far more than 2^64 between key tiles: the lagged-reference softmax
+    (row max of tile j computed in the shadow of its exponentials) must fall back to the exact path for that
+    tile, and a moderate jump (between 2^8 and 2^64) must go through the deferred O/l rescale."""
+    from vface_b200 import ops
+    rng = np.random.default_rng(17)
+    b, n = 2, 448
+    c = heads * d
+    q = rng.standard_normal((b, n, c)).astype(np.float32) * 0.3
+    k = rng.standard_normal((b, n, c)).astype(np.float32) * 0.3
+    v = rng.standard_normal((b, n, c)).astype(np.float32)
+    q[:, 0::3, :] = 2.0                      # every third query row is aligned with the spike keys below
+    k[:, 200, :] = 8.0                       # tile 3: logit = d*16*d^-0.5 (101 nats at d=40) above everything before it
+    k[:, 330, :] = 1.5                       # tile 5: a moderate spike for the other rows' references
+    q[:, 1::3, :] = 1.0
+    k[:, 401, :] = 3.0                       # tile 6: +19 nats for the rows with q = 1 (deferred rescale, no redo)
+    q, k, v = _bf16_round(q), _bf16_round(k), _bf16_round(v)
+    want = ok.attention(q, k, v, heads, d ** -0.5)
+    t = lambda a: torch.from_numpy(a).to(_dev()).bfloat16()
+    got = ops.attention(t(q), t(k), t(v), heads).float().cpu().numpy()
+    assert np.isfinite(got).all()
+    err = np.abs(got - want).max()
+    assert err < BF16_TOL * max(1.0, float(np.abs(want).max()) / 2.0), err
+
+
 def test_attention_full_size_vs_fp32_kernel():
     """BASELINE.json config 3 shape (4096 tokens x 8 heads x d40): tcgen05 path against the fp32 CUDA
     kernel (itself pinned to the oracle above), plus the row-stochastic property: with v = 1 the

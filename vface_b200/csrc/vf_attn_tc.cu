@@ -40,9 +40,11 @@ using namespace sm100;
 
 constexpr int kTcThreads = 256;
 constexpr int kTmaWarp = 4;         // warps 0..3: softmax (one per TMEM lane quarter); 4: TMA producer; 7: MMA issuer
-constexpr int kMmaWarp = 7;
+constexpr int kMmaWarp = 7;         //   (PV issuer; with aliased P the issuer of both chains)
+constexpr int kQkWarp = 6;          // 6: QK issuer in the split-P modes
 constexpr int kBM = 128;            // query rows per CTA
 constexpr float kRescaleThreshold = 8.0f;   // log2 units
+constexpr float kLagGuard = 64.0f;          // log2 units a row may exceed its lagged reference before the exact path
 
 struct AttnTcParams {
   __nv_bfloat16* o;
@@ -50,6 +52,7 @@ struct AttnTcParams {
   int heads, n_q, n_kv, n_kv2, d, d_pad, kb;   // kb = ceil(d / 64) 64-wide head-dim blocks
   float scale_log2;                            // scale * log2(e)
   int spin;                                    // tuning knob: poll instead of suspending on the softmax-side barriers
+  int issue;                                   // MMA issue order in the split-P modes (see the issuer section)
 };
 
 constexpr int kMaxStages = 4;
@@ -57,12 +60,15 @@ constexpr int kMaxStages = 4;
 // Optional phase timing of the softmax warps (build with -DVF_ATTN_TRACE; never in the product build):
 // per-phase clock64 totals of warp 4 of every CTA, summed into g_attn_trace and read with vf_attn_trace_read.
 #ifdef VF_ATTN_TRACE
-__device__ unsigned long long g_attn_trace[16];
+__device__ unsigned long long g_attn_trace[48];
+__device__ unsigned long long g_attn_events[8][16];
+#define VF_EV(j, e) do { if (blockIdx.x == 5 && blockIdx.y == 100 && (j) >= 20 && (j) < 28 && lane == 0) g_attn_events[(j) - 20][e] = clock64(); } while (0)
 #define VF_TR_DECL unsigned long long tr_t = clock64(), tr_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}
 #define VF_TR(i) do { const unsigned long long n_ = clock64(); tr_acc[i] += n_ - tr_t; tr_t = n_; } while (0)
 #else
 #define VF_TR_DECL
 #define VF_TR(i)
+#define VF_EV(j, e)
 #endif
 
 struct __align__(8) TcBarriers {
@@ -84,7 +90,7 @@ template <int kRegs> __device__ __forceinline__ void reg_inc() { asm volatile("s
 // as the softmax threads have loaded it into registers (s_free), so QK_{j+1} is issued while softmax_j is
 // still in its exponentials and the softmax warps never wait for the tensor pipe; PV_j follows when P_j is
 // complete (p_full) and releases P with its own commit (p_empty).  160 TMEM columns -> three CTAs per SM.
-template <int BN, int kTmemCols, int kMinBlocks, int kEmu, int kPMode, int kStages>
+template <int BN, int kTmemCols, int kMinBlocks, int kEmu, int kPMode, int kStages, bool kLagMax>
 __global__ void __launch_bounds__(kTcThreads, kMinBlocks)
 attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                const __grid_constant__ CUtensorMap map_v, const __grid_constant__ CUtensorMap map_k2,
@@ -182,14 +188,20 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
             tma_load_4d(sV + st * kv_bytes + kb * kv_block_bytes, mv, &bars.v_full[st], kb * 64, h, row0, b);
         }
       }
-    } else if (warp == kMmaWarp) {
-      // =========================== MMA issuer ====================================================
+    } else if (warp == kMmaWarp || (kSplitP && warp == kQkWarp && P.issue == 1)) {
+      // =========================== MMA issuer(s) =================================================
       // The issuing warp is the HIGHEST-numbered warp of the CTA (the scheduler arbitrates highest warp id
       // first): a tile needs seven small MMAs and, measured with clock64, a lowest-priority single thread
-      // that competes with three busy softmax warps for issue slots needed ~200 cycles per tcgen05.mma --
-      // 1330 of the 2120 cycles per tile, which made the ISSUER the bound of the kernel, not MUFU or the tensor
-      // pipe.  The loop is warp-uniform (all lanes wait on the barriers, one elected lane issues), so the
+      // that competes with three busy softmax warps for issue slots needed ~200 cycles per tcgen05.mma.
+      // The loop is warp-uniform (all lanes wait on the barriers, one elected lane issues), so the
       // descriptors are computed on the uniform datapath instead of moving through R2UR in front of every MMA.
+      //
+      // Issue order in the split-P modes (P.issue, VF_ATTN_ISSUE):
+      //   0  one issuer, chains back to back:  wait s_free(j) -> QK_{j+1} (k_steps MMAs) ; wait p_full(j) -> PV_j
+      //   1  (default) two issuers: warp 6 the QK chain, warp 7 the PV chain, each with its own commit stream
+      //      (+1..3 %: neither chain queues behind the other's barrier wait).
+      // Measured and dropped: one issuer alternating QK_{j+1} / PV_{j-1} MMAs -- 2x SLOWER in the kernel although
+      // experiments/mma_mix.cu shows the pipe itself does not care about the order (35 clk per MMA SM-wide, 3 CTAs).
       {
         const uint32_t idesc_qk = make_idesc_bf16(kBM, BN, false);
         const uint32_t idesc_pv = make_idesc_bf16(kBM, P.d_pad, true);
@@ -198,57 +210,98 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         const uint32_t k_addr = smem_u32(sK);
         const uint32_t v_addr = smem_u32(sV);
 
+        auto qk_mma = [&](int st, int s) {
+          const uint32_t off_blk = (uint32_t)(s >> 2), off_in = (uint32_t)(s & 3) * 32u;
+          const uint64_t da = make_smem_desc_sw128(q_addr + off_blk * q_block_bytes + off_in, 16, 1024);
+          const uint64_t db = make_smem_desc_sw128(k_addr + st * kv_bytes + off_blk * kv_block_bytes + off_in, 16, 1024);
+          if (elect_one()) mma_ss(tm_s, da, db, idesc_qk, s > 0);
+        };
+        auto pv_mma = [&](int st, int s, bool acc) {
+          // B = V tile, MN-major: 64 head-dim elements contiguous (128 B) per key row, 8-row groups
+          // 1024 B apart (SBO), further 64-wide head-dim blocks kv_block_bytes apart (LBO).
+          const uint64_t db = make_smem_desc_sw128(v_addr + st * kv_bytes + (uint32_t)s * 2048u, kv_block_bytes, 1024);
+          if (elect_one()) mma_ts(tm_o, tm_p + (uint32_t)s * 8u, db, idesc_pv, acc);
+        };
         auto issue_qk = [&](int j) {
           const int st = j % kStages;
           mbar_wait(&bars.k_full[st], (uint32_t)(j / kStages) & 1);
           tc_fence_after();
-          for (int s = 0; s < k_steps; ++s) {
-            const uint32_t off_blk = (uint32_t)(s >> 2), off_in = (uint32_t)(s & 3) * 32u;
-            const uint64_t da = make_smem_desc_sw128(q_addr + off_blk * q_block_bytes + off_in, 16, 1024);
-            const uint64_t db = make_smem_desc_sw128(k_addr + st * kv_bytes + off_blk * kv_block_bytes + off_in, 16, 1024);
-            if (elect_one()) mma_ss(tm_s, da, db, idesc_qk, s > 0);
-          }
+          for (int s = 0; s < k_steps; ++s) qk_mma(st, s);
           if (elect_one()) {
             tc_commit(&bars.k_empty[st]);
             tc_commit(&bars.s_full);
           }
         };
-
-        mbar_wait(&bars.q_full, 0);
-        issue_qk(0);
-        VF_TR_DECL;
-        for (int j = 0; j < n_tiles; ++j) {
+        auto issue_pv = [&](int j) {
           const int st = j % kStages;
-          if (kSplitP && j + 1 < n_tiles) {
-            if (P.spin & 2) mbar_wait_spin(&bars.s_free, (uint32_t)j & 1);
-            else mbar_wait(&bars.s_free, (uint32_t)j & 1);      // S_j is in the softmax threads' registers
-            tc_fence_after();
-            VF_TR(0);                     // MMA thread: wait s_free
-            issue_qk(j + 1);
-            VF_TR(1);                     // issue QK (incl. k_full wait)
-          }
-          mbar_wait(&bars.v_full[st], (uint32_t)(j / kStages) & 1);
-          if (P.spin & 2) mbar_wait_spin(&bars.p_full, (uint32_t)j & 1);
-          else mbar_wait(&bars.p_full, (uint32_t)j & 1);        // P_j in TMEM, O rescaled if needed
-          tc_fence_after();
-          VF_TR(2);                       // wait v_full + p_full
 #pragma unroll
-          for (int s = 0; s < BN / 16; ++s) {
-            // B = V tile, MN-major: 64 head-dim elements contiguous (128 B) per key row, 8-row groups
-            // 1024 B apart (SBO), further 64-wide head-dim blocks kv_block_bytes apart (LBO).
-            const uint64_t db = make_smem_desc_sw128(v_addr + st * kv_bytes + (uint32_t)s * 2048u, kv_block_bytes, 1024);
-            if (elect_one()) mma_ts(tm_o, tm_p + (uint32_t)s * 8u, db, idesc_pv, (j > 0) || (s > 0));
-          }
+          for (int s = 0; s < BN / 16; ++s) pv_mma(st, s, (j > 0) || (s > 0));
           if (elect_one()) tc_commit(&bars.v_empty[st]);
-          if (kSplitP) {
-            if (elect_one()) {
-              tc_commit(&bars.p_empty);
-              if (j + 1 == n_tiles) tc_commit(&bars.o_done);
+        };
+        auto wait_soft = [&](uint64_t* bar, uint32_t parity) {
+          if (P.spin & 2) mbar_wait_spin(bar, parity);
+          else mbar_wait(bar, parity);
+        };
+
+        VF_TR_DECL;
+        if (kSplitP && P.issue == 1 && warp == kQkWarp) {
+          // ---- QK issuer of the two-issuer mode: S_{j+1} as soon as the softmax threads hold S_j ---------
+          mbar_wait(&bars.q_full, 0);
+          issue_qk(0);
+          for (int j = 0; j + 1 < n_tiles; ++j) {
+            wait_soft(&bars.s_free, (uint32_t)j & 1);            // S_j is in the softmax threads' registers
+            tc_fence_after();
+            VF_TR(0);                     // QK issuer: wait s_free
+            VF_EV(j, 8);                  // s_free(j) seen
+            issue_qk(j + 1);
+            VF_EV(j, 9);                  // QK(j+1) issued
+            VF_TR(1);                     // issue QK (incl. k_full wait)
+#ifdef VF_ATTN_TRACE
+            mbar_wait(&bars.s_full, (uint32_t)(j + 1) & 1);     // trace build only: when does S_{j+1} complete?
+            VF_EV(j, 12);
+#endif
+          }
+        } else {
+          // ---- PV issuer of the two-issuer mode / the single sequential issuer ---------------------------
+          const bool both = !(kSplitP && P.issue == 1);
+          if (both) {
+            mbar_wait(&bars.q_full, 0);
+            issue_qk(0);
+          }
+          for (int j = 0; j < n_tiles; ++j) {
+            const int st = j % kStages;
+            if (kSplitP && both && j + 1 < n_tiles) {
+              wait_soft(&bars.s_free, (uint32_t)j & 1);
+              tc_fence_after();
+              VF_TR(0);
+              VF_EV(j, 8);
+              issue_qk(j + 1);
+              VF_EV(j, 9);
+              VF_TR(1);
             }
-            VF_TR(3);                     // issue PV
-          } else {
-            if (j + 1 < n_tiles) issue_qk(j + 1);          // in order behind PV_j: may overwrite P_j
-            else if (elect_one()) tc_commit(&bars.o_done);
+            mbar_wait(&bars.v_full[st], (uint32_t)(j / kStages) & 1);
+            wait_soft(&bars.p_full, (uint32_t)j & 1);              // P_j in TMEM, O rescaled if needed
+            tc_fence_after();
+            VF_TR(2);                       // wait v_full + p_full
+            VF_EV(j, 10);                   // p_full(j) seen
+            issue_pv(j);
+            if (kSplitP) {
+              if (elect_one()) {
+                tc_commit(&bars.p_empty);
+                if (j + 1 == n_tiles) tc_commit(&bars.o_done);
+              }
+              VF_TR(3);                     // issue PV
+              VF_EV(j, 11);                 // PV(j) issued
+#ifdef VF_ATTN_TRACE
+              if (P.issue == 1) {           // trace build only: when does PV_j complete?
+                mbar_wait(&bars.p_empty, (uint32_t)j & 1);
+                VF_EV(j, 13);
+              }
+#endif
+            } else {
+              if (j + 1 < n_tiles) issue_qk(j + 1);          // in order behind PV_j: may overwrite P_j
+              else if (elect_one()) tc_commit(&bars.o_done);
+            }
           }
         }
 #ifdef VF_ATTN_TRACE
@@ -264,6 +317,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
     const int row = q_tile * kBM + quarter * 32 + lane;  // query row owned by this thread
     float m_ref = 0.0f, l = 0.0f;
+    float lag_alpha = 1.0f, lag_m = 0.0f;          // kLagMax: rescale decided by the previous tile's row max
+    bool lag_need = false;
     VF_TR_DECL;
 
     for (int j = 0; j < n_tiles; ++j) {
@@ -276,6 +331,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
       else mbar_wait(&bars.s_full, (uint32_t)j & 1);
       tc_fence_after();
       VF_TR(j == 0 ? 0 : 1);            // 0: prologue until S_0, 1: s_full waits
+      if (warp == 0) VF_EV(j, 0);       // s_full(j) passed
       uint32_t sr[BN];
       tmem_ld_x32(tm_s + lane_off, *reinterpret_cast<uint32_t(*)[32]>(&sr[0]));
       if (BN == 64) tmem_ld_x32(tm_s + lane_off + 32, *reinterpret_cast<uint32_t(*)[32]>(&sr[32]));
@@ -294,63 +350,115 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         if (lane == 0) mbar_arrive(&bars.s_free);
       }
       VF_TR(2);                         // S load (+ deferred P hand-over)
+      if (warp == 0) VF_EV(j, 1);       // s_free(j) arrived (and p_full(j-1))
 
       if (valid < BN) {
 #pragma unroll
         for (int i = 0; i < BN; ++i)
           if (i >= valid) sr[i] = 0xff800000u;   // -inf
       }
-      // row max: 3-input FMNMX3 in four independent chains
-      float mx[4];
-#pragma unroll
-      for (int t = 0; t < 4; ++t) mx[t] = __uint_as_float(sr[t]);
-#pragma unroll
-      for (int i = 0; i < BN; i += 8)
-#pragma unroll
-        for (int t = 0; t < 4; ++t)
-          mx[t] = fmax3(mx[t], __uint_as_float(sr[i + 2 * t]), __uint_as_float(sr[i + 2 * t + 1]));
-      const float cand = fmaxf(fmax3(mx[0], mx[1], mx[2]), mx[3]) * P.scale_log2;
-      float alpha = 1.0f;
-      bool need = false;
-      if (j == 0) {
-        m_ref = cand;
-      } else if (cand > m_ref + kRescaleThreshold) {
-        alpha = ex2_approx(m_ref - cand);
-        m_ref = cand;
-        need = true;
-      }
-      VF_TR(3);                         // row max, rescale decision
       // p = exp2(s * c - m_ref): packed FFMA2 for the affine part, MUFU.EX2 per element, packed FADD2
-      // row sums in two independent chains, bf16x2 packing for the P operand.
+      // row sums in two independent chains, bf16x2 packing for the P operand; the row max (3-input FMNMX3 in
+      // four independent chains) either up front or -- kLagMax -- inside the same instruction stream.
       const uint64_t c2 = pack2(P.scale_log2, P.scale_log2);
-      const uint64_t nm2 = pack2(-m_ref, -m_ref);
       uint64_t acc_a = 0ull, acc_b = 0ull;     // (+0.0f, +0.0f)
       uint32_t pk[BN / 2];
+      float mx[4];
+      auto row_max = [&]() {
 #pragma unroll
-      for (int i = 0; i < BN; i += 4) {
-        const uint64_t xa = ffma2(pack2(__uint_as_float(sr[i + 0]), __uint_as_float(sr[i + 1])), c2, nm2);
-        const uint64_t xb = ffma2(pack2(__uint_as_float(sr[i + 2]), __uint_as_float(sr[i + 3])), c2, nm2);
-        float p0, p1, p2, p3;
-        if (((i / 2) & 3) < kEmu) {
-          exp2_poly2(xa, p0, p1);
-        } else {
-          float t0, t1;
-          unpack2(xa, t0, t1);
-          p0 = ex2_approx(t0); p1 = ex2_approx(t1);
+        for (int t = 0; t < 4; ++t) mx[t] = __uint_as_float(sr[t]);
+#pragma unroll
+        for (int i = 0; i < BN; i += 8)
+#pragma unroll
+          for (int t = 0; t < 4; ++t)
+            mx[t] = fmax3(mx[t], __uint_as_float(sr[i + 2 * t]), __uint_as_float(sr[i + 2 * t + 1]));
+      };
+      auto exps = [&](const bool with_max) {
+        const uint64_t nm2 = pack2(-m_ref, -m_ref);
+        acc_a = 0ull; acc_b = 0ull;
+        if (with_max) {
+#pragma unroll
+          for (int t = 0; t < 4; ++t) mx[t] = __uint_as_float(sr[t]);
         }
-        if (((i / 2 + 1) & 3) < kEmu) {
-          exp2_poly2(xb, p2, p3);
-        } else {
-          float t2, t3;
-          unpack2(xb, t2, t3);
-          p2 = ex2_approx(t2); p3 = ex2_approx(t3);
+#pragma unroll
+        for (int i = 0; i < BN; i += 4) {
+          const uint64_t xa = ffma2(pack2(__uint_as_float(sr[i + 0]), __uint_as_float(sr[i + 1])), c2, nm2);
+          const uint64_t xb = ffma2(pack2(__uint_as_float(sr[i + 2]), __uint_as_float(sr[i + 3])), c2, nm2);
+          if (with_max) {
+            mx[(i / 4) & 3] = fmax3(mx[(i / 4) & 3], __uint_as_float(sr[i + 0]), __uint_as_float(sr[i + 1]));
+            mx[(i / 4 + 2) & 3] = fmax3(mx[(i / 4 + 2) & 3], __uint_as_float(sr[i + 2]), __uint_as_float(sr[i + 3]));
+          }
+          float p0, p1, p2, p3;
+          if (((i / 2) & 3) < kEmu) {
+            exp2_poly2(xa, p0, p1);
+          } else {
+            float t0, t1;
+            unpack2(xa, t0, t1);
+            p0 = ex2_approx(t0); p1 = ex2_approx(t1);
+          }
+          if (((i / 2 + 1) & 3) < kEmu) {
+            exp2_poly2(xb, p2, p3);
+          } else {
+            float t2, t3;
+            unpack2(xb, t2, t3);
+            p2 = ex2_approx(t2); p3 = ex2_approx(t3);
+          }
+          acc_a = fadd2(acc_a, pack2(p0, p1));
+          acc_b = fadd2(acc_b, pack2(p2, p3));
+          pk[i / 2 + 0] = pack_bf16(p0, p1);
+          pk[i / 2 + 1] = pack_bf16(p2, p3);
         }
-        acc_a = fadd2(acc_a, pack2(p0, p1));
-        acc_b = fadd2(acc_b, pack2(p2, p3));
-        pk[i / 2 + 0] = pack_bf16(p0, p1);
-        pk[i / 2 + 1] = pack_bf16(p2, p3);
+      };
+      float alpha = 1.0f;
+      bool need = false;
+      if (!kLagMax) {
+        row_max();
+        const float cand = fmaxf(fmax3(mx[0], mx[1], mx[2]), mx[3]) * P.scale_log2;
+        if (j == 0) {
+          m_ref = cand;
+        } else if (cand > m_ref + kRescaleThreshold) {
+          alpha = ex2_approx(m_ref - cand);
+          m_ref = cand;
+          need = true;
+        }
+        VF_TR(3);                         // row max, rescale decision
+        exps(false);
+      } else {
+        // Lagged reference: the exponentials of tile j use the reference decided from tiles < j (lag_alpha /
+        // lag_need carry the O, l rescale that decision implies), while this tile's row max is computed in the
+        // shadow of the MUFU stream and only decides the reference of tile j+1.  P_j may then exceed 1 -- by at
+        // most 2^kLagGuard, harmless in bf16/fp32 -- and a row that jumps further (or tile 0, which has no
+        // reference yet) takes the exact path: max first, exponentials again.  The result is the same softmax.
+        alpha = lag_alpha;
+        need = lag_need;
+        bool redo = j == 0;
+        if (!redo) {
+          exps(true);
+        } else {
+          row_max();
+        }
+        const float cand = fmaxf(fmax3(mx[0], mx[1], mx[2]), mx[3]) * P.scale_log2;
+        if (!redo) redo = __any_sync(0xffffffffu, cand > m_ref + kLagGuard);
+        if (redo) {
+          if (j == 0) {
+            m_ref = cand;
+          } else if (cand > m_ref + kRescaleThreshold) {
+            alpha *= ex2_approx(m_ref - cand);
+            m_ref = cand;
+            need = true;
+          }
+          exps(false);
+        }
+        lag_alpha = 1.0f;
+        lag_need = false;
+        if (cand > m_ref + kRescaleThreshold) {     // decided now, applied to tile j+1 (its exps, then O and l)
+          lag_alpha = ex2_approx(m_ref - cand);
+          lag_m = cand;
+          lag_need = true;
+        }
       }
       VF_TR(4);                         // exponentials
+      if (warp == 0) VF_EV(j, 2);       // exps done
       if (kSplitP && j > 0) {              // PV_{j-1} still reads P (and writes O) until its commit
         if (P.spin) mbar_wait_spin(&bars.p_empty, (uint32_t)(j - 1) & 1);
         else mbar_wait(&bars.p_empty, (uint32_t)(j - 1) & 1);
@@ -367,6 +475,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
       unpack2(acc_a, sa0, sa1);
       unpack2(acc_b, sb0, sb1);
       l = l * alpha + ((sa0 + sa1) + (sb0 + sb1));
+      if (kLagMax && lag_need) m_ref = lag_m;      // reference of the next tile
       if (j > 0 && __any_sync(0xffffffffu, need)) {
         for (int c = 0; c < P.d; c += 8) {
           uint32_t o8[8];
@@ -378,6 +487,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         }
       }
       VF_TR(6);                         // P store, row sums, rare O rescale
+      if (warp == 0) VF_EV(j, 3);       // tile done
       if (!kSplitP || j + 1 == n_tiles) {
         tmem_wait_st();
         tc_fence_before();
@@ -413,6 +523,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
       atomicAdd(&g_attn_trace[8], 1ull);
       atomicAdd(&g_attn_trace[9], (unsigned long long)n_tiles);
     }
+    if (lane == 0) for (int i = 0; i < 8; ++i) atomicAdd(&g_attn_trace[16 + warp * 8 + i], tr_acc[i]);   // per quarter
 #endif
   }
 
@@ -456,17 +567,17 @@ static int make_map(CUtensorMap* m, const void* base, int batch, int heads, int 
   return 0;
 }
 
-template <int BN, int kTmemCols, int kMinBlocks, int kEmu, int kPMode = 0, int kStages = 2>
+template <int BN, int kTmemCols, int kMinBlocks, int kEmu, int kPMode = 0, int kStages = 2, bool kLagMax = false>
 static int launch_tc(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const CUtensorMap& mk2,
                      const CUtensorMap& mv2, const AttnTcParams& P, int batch, cudaStream_t st) {
   const size_t smem = 1024 + (size_t)P.kb * (kBM * 128 + 2 * kStages * BN * 128);
   static bool attr = false;
   if (!attr) {
-    VF_CUDA_TRY(cudaFuncSetAttribute(attn_tc_kernel<BN, kTmemCols, kMinBlocks, kEmu, kPMode, kStages>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    VF_CUDA_TRY(cudaFuncSetAttribute(attn_tc_kernel<BN, kTmemCols, kMinBlocks, kEmu, kPMode, kStages, kLagMax>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr = true;
   }
   dim3 grid((P.n_q + kBM - 1) / kBM, batch * P.heads);
-  attn_tc_kernel<BN, kTmemCols, kMinBlocks, kEmu, kPMode, kStages><<<grid, kTcThreads, smem, st>>>(mq, mk, mv, mk2, mv2, P);
+  attn_tc_kernel<BN, kTmemCols, kMinBlocks, kEmu, kPMode, kStages, kLagMax><<<grid, kTcThreads, smem, st>>>(mq, mk, mv, mk2, mv2, P);
   return check_cuda(cudaGetLastError(), "attn_tc_kernel launch");
 }
 
@@ -498,6 +609,9 @@ int launch_attn_tc(const void* q, const void* k, const void* v, void* o, int bat
     static int spin = -1;
     if (spin < 0) { const char* e = getenv("VF_ATTN_SPIN"); spin = e ? atoi(e) : 0; }
     P.spin = spin;
+    static int issue = -1;
+    if (issue < 0) { const char* e = getenv("VF_ATTN_ISSUE"); issue = e ? atoi(e) : 1; }
+    P.issue = issue;
   }
   static int emu = -1;      // tuning knob: VF_ATTN_EMU = 0..3 pairs of every 4 on the FMA pipe
   if (emu < 0) {
@@ -512,6 +626,13 @@ int launch_attn_tc(const void* q, const void* k, const void* v, void* o, int bat
   if (split < 0) {
     const char* e = getenv("VF_ATTN_SPLITP");
     split = e ? atoi(e) : 1;
+  }
+  // VF_ATTN_LAGMAX: 1 = row max of tile j in the shadow of its exponentials (lagged reference); 0 (default) = max first.
+  // Measured equal within 1 % (gpurun_out/lagmax_ab.log): the row max is not on the kernel's critical resource.
+  static int lag = -1;
+  if (lag < 0) {
+    const char* e = getenv("VF_ATTN_LAGMAX");
+    lag = e ? atoi(e) : 0;
   }
   const bool bn48 = split == 3 && P.d_pad <= 48;
   const int bn = bn48 ? 48 : 64;
@@ -537,7 +658,9 @@ int launch_attn_tc(const void* q, const void* k, const void* v, void* o, int bat
     switch (emu) {
       case 1: return launch_tc<64, 128, 3, 1, 1>(mq, mk, mv, mk2, mv2, P, batch, st);
       case 2: return launch_tc<64, 128, 3, 2, 1>(mq, mk, mv, mk2, mv2, P, batch, st);
-      default: return launch_tc<64, 128, 3, 0, 1>(mq, mk, mv, mk2, mv2, P, batch, st);
+      default:
+        if (lag) return launch_tc<64, 128, 3, 0, 1, 2, true>(mq, mk, mv, mk2, mv2, P, batch, st);
+        return launch_tc<64, 128, 3, 0, 1>(mq, mk, mv, mk2, mv2, P, batch, st);
     }
   }
   if (P.d_pad <= 64) {                                                                   // 48 KB smem: 4 CTAs / SM
@@ -551,7 +674,10 @@ int launch_attn_tc(const void* q, const void* k, const void* v, void* o, int bat
   }
   // d in (64, 192]: 256 TMEM columns, two CTAs/SM.  Up to d = 160 (the UNet's 80 and 160) P sits behind O in
   // the same allocation (S 64 | O 160 | P 32) so QK_{j+1} is issued early as in the d <= 64 kernel.
-  if (split && P.d_pad <= 160) return launch_tc<64, 256, 2, 0, 2>(mq, mk, mv, mk2, mv2, P, batch, st);
+  if (split && P.d_pad <= 160) {
+    if (lag) return launch_tc<64, 256, 2, 0, 2, 2, true>(mq, mk, mv, mk2, mv2, P, batch, st);
+    return launch_tc<64, 256, 2, 0, 2>(mq, mk, mv, mk2, mv2, P, batch, st);
+  }
   return launch_tc<64, 256, 2, 0>(mq, mk, mv, mk2, mv2, P, batch, st);
 }
 
@@ -559,9 +685,10 @@ int launch_attn_tc(const void* q, const void* k, const void* v, void* o, int bat
 
 #ifdef VF_ATTN_TRACE
 extern "C" int vf_attn_trace_read(unsigned long long* out16, int reset) {
-  if (cudaMemcpyFromSymbol(out16, vf::g_attn_trace, sizeof(unsigned long long) * 16) != cudaSuccess) return 1;
+  if (reset == 2) return cudaMemcpyFromSymbol(out16, vf::g_attn_events, sizeof(unsigned long long) * 128) != cudaSuccess;
+  if (cudaMemcpyFromSymbol(out16, vf::g_attn_trace, sizeof(unsigned long long) * 48) != cudaSuccess) return 1;
   if (reset) {
-    unsigned long long z[16] = {0};
+    unsigned long long z[48] = {0};
     if (cudaMemcpyToSymbol(vf::g_attn_trace, z, sizeof(z)) != cudaSuccess) return 1;
   }
   return 0;
