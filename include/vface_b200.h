@@ -28,7 +28,7 @@ extern "C" {
 #define VF_F32 0
 #define VF_BF16 1
 
-#define VF_ABI_VERSION 5
+#define VF_ABI_VERSION 7
 
 /* ABI version of the loaded library (== VF_ABI_VERSION). */
 int vf_abi_version(void);
@@ -193,6 +193,29 @@ int vf_add_bias(const void* a, const void* b, const void* bias, long long rows_p
  * (ldm/modules/diffusionmodules/openaimodel.py:107-117; also model.py:52-56 of the first-stage decoder).
  */
 int vf_upsample_nearest2x_nhwc(const void* x, void* out, int n, int h, int w, int c, int dtype, void* stream);
+
+/*
+ * Output convolution of the UNet with an fp32 result: eps = conv3x3(x, weight, padding 1) + bias,
+ *   x (n, h, w, c) channels-last bf16, weight (c_out = 4, c, 3, 3) contiguous OIHW bf16, bias (4) bf16 or NULL,
+ *   out (n, 4, h, w) contiguous fp32.
+ * Replaces the last layer of `self.out` (ldm/modules/diffusionmodules/openaimodel.py:835, applied at :907) on the bf16
+ * path: the classifier-free-guidance combination (ldm/models/diffusion/ddim_w_inv.py:666) multiplies the rounding of a
+ * bf16 eps by 3.6, so eps leaves the UNet in fp32.  The fp32 path keeps the library convolution.
+ */
+int vf_conv3x3_out_f32(const void* x, const void* weight, const void* bias, void* out, int n, int h, int w, int c,
+                       int c_out, int dtype, void* stream);
+
+/*
+ * Projection with bias and residual add inside one library GEMM (cuBLASLt, beta = 1, bias epilogue):
+ *   out[r, 0:n] = residual[r, 0:n] + x[r, 0:k] . W^T + bias,   W (n, k) row-major, bias (n) or NULL.
+ * Replaces `x = ff(norm3(x)) + x` (ldm/modules/attention.py:242: FeedForward's down-projection, :61-64, plus the add)
+ * and `proj_out(x) + x_in` (attention.py:287-288).  out must not alias residual (measured: the library's in-place
+ * path rounds differently by one bf16 ulp).  Row strides in elements; the caller owns
+ * `workspace` (workspace_bytes may be 0).  dtype VF_BF16 or VF_F32 (fp32 accumulation either way).
+ */
+int vf_linear_residual(const void* x, const void* w, const void* bias, const void* residual, void* out,
+                       long long rows, int k, int n, long long ld_x, long long ld_res, long long ld_out,
+                       void* workspace, long long workspace_bytes, int dtype, void* stream);
 
 #ifdef __cplusplus
 }

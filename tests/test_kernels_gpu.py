@@ -404,3 +404,44 @@ def test_upsample_nearest2x_matches_interpolate(dtype):
     want = torch.nn.functional.interpolate(x, scale_factor=2, mode="nearest")
     assert got.shape == want.shape and torch.equal(got, want)
     assert got.is_contiguous(memory_format=torch.channels_last)
+
+
+@pytest.mark.parametrize("n,h,w,c", [(3, 64, 64, 320), (2, 20, 13, 64), (1, 8, 8, 32)])
+def test_conv3x3_out_f32_matches_fp32_convolution(n, h, w, c):
+    """The fp32-output final convolution against torch's fp32 conv2d on the same bf16-valued inputs (ragged tiles,
+    image borders, bias)."""
+    import torch.nn.functional as F
+    from vface_b200 import ops
+    g = torch.Generator().manual_seed(c + h)
+    x = torch.randn(n, h, w, c, generator=g).bfloat16().to(_dev())
+    conv = torch.nn.Conv2d(c, 4, 3, padding=1)
+    with torch.no_grad():
+        conv.weight.copy_(torch.randn(4, c, 3, 3, generator=g) / (9 * c) ** 0.5)
+        conv.bias.copy_(torch.randn(4, generator=g))
+    conv = conv.to(_dev()).bfloat16().to(memory_format=torch.channels_last)
+    got = ops.conv3x3_out_f32(x, conv)
+    assert got.dtype == torch.float32 and tuple(got.shape) == (n, 4, h, w) and got.is_contiguous()
+    with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+        want = F.conv2d(x.float().permute(0, 3, 1, 2), conv.weight.float(), conv.bias.float(), padding=1)
+    assert (got - want).abs().max().item() < 2e-5 * max(1.0, want.abs().max().item())
+
+
+@pytest.mark.parametrize("rows,k,n", [(4096 * 3, 1280, 320), (1000, 320, 320), (256 * 3, 5120, 1280)])
+@pytest.mark.parametrize("bf16", [True, False])
+def test_linear_residual(rows, k, n, bf16):
+    """residual + x W^T + bias in one library GEMM against the fp32 evaluation of the same expression."""
+    from vface_b200 import ops
+    g = torch.Generator().manual_seed(rows + k)
+    dt = torch.bfloat16 if bf16 else torch.float32
+    x = torch.randn(rows, k, generator=g).to(dt).to(_dev())
+    w = (torch.randn(n, k, generator=g) / k ** 0.5).to(dt).to(_dev())
+    b = torch.randn(n, generator=g).to(dt).to(_dev())
+    r = torch.randn(rows, n, generator=g).to(dt).to(_dev())
+    want = r.double() + x.double() @ w.double().t() + b.double()
+    got = ops.linear_residual(x, w, b, r)
+    assert got.data_ptr() != r.data_ptr()
+    tol = BF16_TOL if bf16 else 2e-5
+    assert (got.double() - want).abs().max().item() < tol * max(1.0, want.abs().max().item() / 2.0)
+    got_nb = ops.linear_residual(x, w, None, r)
+    assert (got_nb.double() - (want - b.double())).abs().max().item() < tol * max(1.0, want.abs().max().item() / 2.0)
+    assert torch.equal(ops.linear_residual(x, w, b, r), got)       # run-to-run reproducible

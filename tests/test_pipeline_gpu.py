@@ -73,6 +73,26 @@ def test_sampler_small_vs_reference_golden(kind, dtype, tol):
     assert rel_l2(px0[S // 2:], want0[S // 2:]) < tol
 
 
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-4), (torch.bfloat16, 1e-2)])
+def test_sampler_full_size_vs_reference_golden(dtype, tol):
+    """The FULL-SIZE UNet (859.5 M parameters) through DDIMSampler.sample: 2 frames, 5 DDIM steps, CFG 3.0, hooks on
+    (FSAI on six modules, flow warp on the two 64x64 ones): every per-step latent against the unmodified reference
+    run on CPU (tests/golden/sampler_full.npz, oracle/make_golden.py::golden_sampler_full)."""
+    from oracle import kernels as ok
+    from vface_b200 import synth
+    gold = np.load(os.path.join(GOLD, "sampler_full.npz"))
+    _, sampler, _ = build(None, dtype)
+    S, B = 5, 2
+    clip = synth.synth_clip(B, steps=ok.make_schedule(S)["ddim_timesteps"], flow_kind="smooth")
+    samples, inter = run_sample(sampler, clip, S, B, clip["inversion"])
+    want = gold["x_inter"]
+    assert float(np.abs(want[-1] - want[0]).mean()) > 0.05          # the trajectory moves: not a vacuous comparison
+    for i in range(S):
+        err = rel_l2(inter["x_inter"][1 + i], want[i])
+        assert err < tol, (i, err)
+    assert rel_l2(samples, gold["samples"]) < tol
+
+
 def test_inversion_dir_and_dict_agree(tmp_path):
     """The reference's on-disk format (ddim_latents_{t}.pt per step) and the in-memory hand-off give
     identical samples."""

@@ -18,7 +18,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ_DIR = os.path.join(HERE, "csrc", "build")
 LIB_PATH = os.path.join(HERE, "libvface_b200.so")
 
-SOURCES = ["vf_capi.cu", "vf_ddim.cu", "vf_flow_warp.cu", "vf_fsai.cu", "vf_attn.cu", "vf_attn_f32.cu", "vf_attn_tc.cu", "vf_norm.cu", "vf_gemm.cu"]
+SOURCES = ["vf_capi.cu", "vf_ddim.cu", "vf_flow_warp.cu", "vf_fsai.cu", "vf_attn.cu", "vf_attn_f32.cu", "vf_attn_tc.cu", "vf_norm.cu", "vf_gemm.cu", "vf_conv_out.cu", "vf_linear.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -67,7 +67,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     with cf.ThreadPoolExecutor(max_workers=min(8, len(SOURCES))) as ex:
         objs = list(ex.map(lambda s: _compile(nvcc, s, verbose), SOURCES))
     tmp = LIB_PATH + ".tmp"
-    cmd = [nvcc, "-shared", "-o", tmp, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-lcudart_static", "-ldl", "-lrt", "-lpthread"]
+    cmd = [nvcc, "-shared", "-o", tmp, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-lcudart_static", "-lcublasLt", "-ldl", "-lrt", "-lpthread"]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError(f"link failed:\n{res.stdout}\n{res.stderr}")

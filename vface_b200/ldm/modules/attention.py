@@ -160,6 +160,16 @@ class BasicTransformerBlock(nn.Module):
             x, n2 = ln(self.norm2, x, y=a1.contiguous())
             a2 = self.attn2(n2, context=context)
             x, n3 = ln(self.norm3, x, y=a2.contiguous())
+        return self._ff_residual(x, n3)
+
+    def _ff_residual(self, x, n3):
+        """x + ff(n3).  bf16 with the reference's GEGLU feed-forward: the down-projection, its bias and the residual add
+        are ONE library GEMM (beta = 1), so ff(n3) is never rounded and written out on its own."""
+        net = self.ff.net
+        if (x.dtype == torch.bfloat16 and isinstance(net[0], GEGLU) and isinstance(net[2], nn.Linear)
+                and "forward" not in self.ff.__dict__ and net[2].weight.is_contiguous()):
+            h = net[0](n3)                                  # Dropout(p) of an eval-mode network is the identity
+            return ops.linear_residual(h.contiguous(), net[2].weight, net[2].bias, x)
         return ops.add_bias(x, self.ff(n3))
 
 
@@ -187,6 +197,9 @@ class SpatialTransformer(nn.Module):
         t = F.linear(g, self.proj_in.weight.reshape(self.proj_in.out_channels, c), self.proj_in.bias)   # 1x1 conv
         for block in self.transformer_blocks:
             t = block(t, context=context)
-        o = F.linear(t, self.proj_out.weight.reshape(c, -1), self.proj_out.bias)                        # 1x1 conv
-        out = ops.add_bias(o, tok)
+        w_out = self.proj_out.weight.reshape(c, -1)                                                     # 1x1 conv
+        if t.dtype == torch.bfloat16 and w_out.is_contiguous():
+            out = ops.linear_residual(t.contiguous(), w_out, self.proj_out.bias, tok)    # proj_out(t) + x_in in one GEMM
+        else:
+            out = ops.add_bias(F.linear(t, w_out, self.proj_out.bias), tok)
         return out.view(b, h, w, c).permute(0, 3, 1, 2)

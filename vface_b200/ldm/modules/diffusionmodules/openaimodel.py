@@ -280,5 +280,9 @@ class UNetModel(nn.Module):
                 features.append(h)
         gn = self.out[0]
         ht = ops.group_norm_nhwc(h.permute(0, 2, 3, 1).contiguous(), gn.weight, gn.bias, gn.eps, gn.num_groups, silu=True)
-        out = ops.conv2d_nhwc(ht.permute(0, 3, 1, 2), self.out[2]).to(x.dtype).contiguous()
+        conv = self.out[2]
+        if dt == torch.bfloat16 and conv.out_channels == 4 and conv.in_channels % 32 == 0 and x.dtype == torch.float32:
+            out = ops.conv3x3_out_f32(ht, conv)              # eps in fp32: CFG multiplies a bf16 rounding by 3.6
+        else:
+            out = ops.conv2d_nhwc(ht.permute(0, 3, 1, 2), conv).to(x.dtype).contiguous()
         return (out, features) if return_features else out

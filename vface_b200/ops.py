@@ -391,6 +391,55 @@ def conv2d_nhwc(x: torch.Tensor, conv) -> torch.Tensor:
     return y
 
 
+_lt_workspace = {}
+
+
+def linear_residual(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], residual: torch.Tensor) -> torch.Tensor:
+    """residual + x @ weight^T + bias in ONE library GEMM (cuBLASLt: beta = 1 and the bias in the fp32 epilogue), for
+    `x = ff(norm3(x)) + x` (attention.py:242) and `proj_out(x) + x_in` (attention.py:287-288): the projection is never
+    rounded and written out just to be re-read by an add.  Returns a new tensor; `residual` is not modified."""
+    _need_cuda(x, weight, bias, residual)
+    n, k = weight.shape
+    if x.shape[-1] != k or residual.shape[-1] != n or x.shape[:-1] != residual.shape[:-1]:
+        raise ValueError(f"linear_residual: shapes x {tuple(x.shape)}, weight {tuple(weight.shape)}, residual {tuple(residual.shape)}")
+    if not (x.is_contiguous() and weight.is_contiguous() and residual.is_contiguous()):
+        raise ValueError("linear_residual: contiguous tensors")
+    if weight.dtype != x.dtype or residual.dtype != x.dtype or (bias is not None and bias.dtype != x.dtype):
+        raise ValueError("linear_residual: one dtype")
+    out = torch.empty_like(residual)
+    ws = _lt_workspace.get(x.device)
+    if ws is None:
+        ws = _lt_workspace[x.device] = torch.empty(32 << 20, dtype=torch.uint8, device=x.device)
+    rows = x.numel() // k
+    lib = _lib.load()
+    rc = lib.vf_linear_residual(x.data_ptr(), weight.data_ptr(), bias.data_ptr() if bias is not None else None,
+                                residual.data_ptr(), out.data_ptr(), rows, k, n, k, n, n, ws.data_ptr(), ws.numel(),
+                                _code(x), _stream(x))
+    _lib.check(rc, "vf_linear_residual")          # a library GEMM: not counted as a vface_b200 kernel launch
+    return out
+
+
+def conv3x3_out_f32(x_nhwc: torch.Tensor, conv) -> torch.Tensor:
+    """The UNet's output convolution (openaimodel.py:835/:907) with an fp32 result: x_nhwc (n, h, w, c) bf16
+    channels-last tokens -> (n, 4, h, w) fp32 contiguous.  eps leaves the network unrounded because classifier-free
+    guidance multiplies the rounding of a bf16 eps by 3.6 (ddim_w_inv.py:666)."""
+    _need_cuda(x_nhwc, conv.weight)
+    if x_nhwc.dtype != torch.bfloat16 or not x_nhwc.is_contiguous():
+        raise ValueError("conv3x3_out_f32: contiguous bf16 (n, h, w, c) input")
+    if conv.kernel_size != (3, 3) or conv.stride != (1, 1) or conv.padding != (1, 1) or conv.groups != 1:
+        raise ValueError("conv3x3_out_f32: 3x3, stride 1, padding 1 convolution")
+    n, h, w, c = x_nhwc.shape
+    wt = conv.weight.detach().contiguous()                         # OIHW (tiny: 4 x c x 9)
+    bias = conv.bias.detach().contiguous() if conv.bias is not None else None
+    out = torch.empty((n, wt.shape[0], h, w), dtype=torch.float32, device=x_nhwc.device)
+    lib = _lib.load()
+    rc = lib.vf_conv3x3_out_f32(x_nhwc.data_ptr(), wt.data_ptr(), bias.data_ptr() if bias is not None else None,
+                                out.data_ptr(), n, h, w, c, wt.shape[0], _code(x_nhwc), _stream(x_nhwc))
+    _lib.check(rc, "vf_conv3x3_out_f32")
+    _count()
+    return out
+
+
 def add_bias(a: torch.Tensor, b: Optional[torch.Tensor] = None, row_bias: Optional[torch.Tensor] = None,
              out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """a + b + row_bias over contiguous (..., c) tensors; row_bias (c,) or (n, c).  out may be `a` (in place)."""
