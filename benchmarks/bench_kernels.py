@@ -159,6 +159,11 @@ def bench_glue(res, iters):
         y = rn(b, n, c)
         rec(f"add_bias rows={b * n} c={c}", lambda: ops.add_bias(x, y, bb), 3.0 * b * n * c * e)
         rec(f"add+layer_norm rows={b * n} c={c} (2 reads + 2 writes)", lambda: ops.add_layer_norm(x, w, bb, 1e-5, y=y), 4.0 * b * n * c * e)
+        rec(f"layer_norm rows={b * n} c={c} (1 read + 1 write)", lambda: ops.add_layer_norm(x, w, bb, 1e-5), 2.0 * b * n * c * e)
+    # output convolution with an fp32 result (9 c 4 MAC per pixel; reads x once, writes 4 fp32 per pixel)
+    conv = torch.nn.Conv2d(320, 4, 3, padding=1).cuda().bfloat16()
+    xo = rn(96, 64, 64, 320)
+    rec("conv3x3 320->4, fp32 out, n=96 64x64 (1 read of x)", lambda: ops.conv3x3_out_f32(xo, conv), 96 * 4096 * (320 * e + 16.0))
     x1, x2 = rn(96, 4096, 320), rn(96, 4096, 320)
     w, bb = rn(640), rn(640)
     rec("group_norm+silu over cat(320+320) n=96 hw=4096", lambda: ops.group_norm_nhwc(x1, w, bb, 1e-5, 32, silu=True, x2=x2),

@@ -28,7 +28,7 @@ extern "C" {
 #define VF_F32 0
 #define VF_BF16 1
 
-#define VF_ABI_VERSION 7
+#define VF_ABI_VERSION 8
 
 /* ABI version of the loaded library (== VF_ABI_VERSION). */
 int vf_abi_version(void);
@@ -216,6 +216,16 @@ int vf_conv3x3_out_f32(const void* x, const void* weight, const void* bias, void
 int vf_linear_residual(const void* x, const void* w, const void* bias, const void* residual, void* out,
                        long long rows, int k, int n, long long ld_x, long long ld_res, long long ld_out,
                        void* workspace, long long workspace_bytes, int dtype, void* stream);
+
+/*
+ * The same with a bias per batch entry: x, residual, out hold `batch` entries of `rows` rows each (contiguous per
+ * entry), bias is (batch, n).  Replaces `x = attn1(norm1(x)) + x ; x = attn2(norm2(x), ctx) + x`
+ * (ldm/modules/attention.py:240-241) when the context is a single token: attn2's output is then one row per sample,
+ * which rides in the bias of the to_out projection of attn1 (to_out: attention.py:173-176).
+ */
+int vf_linear_residual_batched(const void* x, const void* w, const void* bias, const void* residual, void* out,
+                               int batch, long long rows, int k, int n, long long ld_x, long long ld_res, long long ld_out,
+                               void* workspace, long long workspace_bytes, int dtype, void* stream);
 
 #ifdef __cplusplus
 }

@@ -26,7 +26,7 @@ struct LtPlan {
 
 static cublasLtHandle_t g_lt = nullptr;
 static std::mutex g_lt_mutex;
-static std::map<std::tuple<long long, int, int, long long, long long, long long, int, int>, LtPlan> g_plans;
+static std::map<std::tuple<long long, int, int, long long, long long, long long, int, int, int>, LtPlan> g_plans;
 
 static int lt_fail(cublasStatus_t s, const char* what) { return fail("vf_linear_residual: %s failed with cublasStatus %d", what, (int)s); }
 
@@ -36,8 +36,17 @@ static int lt_fail(cublasStatus_t s, const char* what) { return fail("vf_linear_
     if (_s != CUBLAS_STATUS_SUCCESS) return lt_fail(_s, #expr);            \
   } while (0)
 
+static int set_batch(cublasLtMatrixLayout_t l, int batch, long long stride) {
+  const int32_t b = batch;
+  const int64_t st = stride;
+  VF_LT_TRY(cublasLtMatrixLayoutSetAttribute(l, CUBLASLT_MATRIX_LAYOUT_BATCH_COUNT, &b, sizeof(b)));
+  VF_LT_TRY(cublasLtMatrixLayoutSetAttribute(l, CUBLASLT_MATRIX_LAYOUT_STRIDED_BATCH_OFFSET, &st, sizeof(st)));
+  return 0;
+}
+
+// batch > 1: `rows` rows per batch entry, entries contiguous (stride rows * ld), W shared, bias (batch, n).
 static int make_plan(LtPlan& P, long long rows, int k, int n, long long ld_x, long long ld_res, long long ld_out, int dtype,
-                     bool has_bias, size_t ws_bytes) {
+                     bool has_bias, size_t ws_bytes, int batch) {
   const cudaDataType_t dt = dtype == VF_BF16 ? CUDA_R_16BF : CUDA_R_32F;
   VF_LT_TRY(cublasLtMatmulDescCreate(&P.op, CUBLAS_COMPUTE_32F, CUDA_R_32F));
   // row-major out (rows, n) = x (rows, k) . W^T  <=>  column-major out^T (n, rows) = W (k, n)^T . x^T (k, rows)
@@ -54,6 +63,16 @@ static int make_plan(LtPlan& P, long long rows, int k, int n, long long ld_x, lo
   VF_LT_TRY(cublasLtMatrixLayoutCreate(&P.c, dt, (uint64_t)n, (uint64_t)rows, (int64_t)ld_res));
   cublasLtMatrixLayout_t d = nullptr;
   VF_LT_TRY(cublasLtMatrixLayoutCreate(&d, dt, (uint64_t)n, (uint64_t)rows, (int64_t)ld_out));
+  if (batch > 1) {
+    if (int rc = set_batch(P.a, batch, 0)) return rc;
+    if (int rc = set_batch(P.b, batch, rows * ld_x)) return rc;
+    if (int rc = set_batch(P.c, batch, rows * ld_res)) return rc;
+    if (int rc = set_batch(d, batch, rows * ld_out)) return rc;
+    if (has_bias) {
+      const int64_t bs = n;
+      VF_LT_TRY(cublasLtMatmulDescSetAttribute(P.op, CUBLASLT_MATMUL_DESC_BIAS_BATCH_STRIDE, &bs, sizeof(bs)));
+    }
+  }
   cublasLtMatmulPreference_t pref = nullptr;
   VF_LT_TRY(cublasLtMatmulPreferenceCreate(&pref));
   VF_LT_TRY(cublasLtMatmulPreferenceSetAttribute(pref, CUBLASLT_MATMUL_PREF_MAX_WORKSPACE_BYTES, &ws_bytes, sizeof(ws_bytes)));
@@ -71,14 +90,14 @@ static int make_plan(LtPlan& P, long long rows, int k, int n, long long ld_x, lo
 
 }  // namespace vf
 
-extern "C" int vf_linear_residual(const void* x, const void* w, const void* bias, const void* residual, void* out,
-                                  long long rows, int k, int n, long long ld_x, long long ld_res, long long ld_out,
-                                  void* workspace, long long workspace_bytes, int dtype, void* stream) {
+static int linear_residual_impl(const void* x, const void* w, const void* bias, const void* residual, void* out, int batch,
+                                long long rows, int k, int n, long long ld_x, long long ld_res, long long ld_out,
+                                void* workspace, long long workspace_bytes, int dtype, void* stream) {
   using namespace vf;
   if (int rc = check_device()) return rc;
   if (!x || !w || !residual || !out) return fail("vf_linear_residual: null pointer");
   if (dtype != VF_BF16 && dtype != VF_F32) return fail("vf_linear_residual: bad dtype %d", dtype);
-  if (rows <= 0 || k <= 0 || n <= 0) return fail("vf_linear_residual: bad shape rows=%lld k=%d n=%d", rows, k, n);
+  if (rows <= 0 || k <= 0 || n <= 0 || batch < 1) return fail("vf_linear_residual: bad shape batch=%d rows=%lld k=%d n=%d", batch, rows, k, n);
   if (ld_x < k || ld_res < n || ld_out < n) return fail("vf_linear_residual: row strides smaller than the row length");
   const void* ptrs[4] = {x, w, residual, out};
   for (const void* p : ptrs)
@@ -90,11 +109,11 @@ extern "C" int vf_linear_residual(const void* x, const void* w, const void* bias
   {
     std::lock_guard<std::mutex> lock(g_lt_mutex);
     if (!g_lt) VF_LT_TRY(cublasLtCreate(&g_lt));
-    const auto key = std::make_tuple(rows, k, n, ld_x, ld_res, ld_out, dtype * 2 + (bias ? 1 : 0), (int)(workspace_bytes >> 20));
+    const auto key = std::make_tuple(rows, k, n, ld_x, ld_res, ld_out, dtype * 2 + (bias ? 1 : 0), (int)(workspace_bytes >> 20), batch);
     auto it = g_plans.find(key);
     if (it == g_plans.end()) {
       LtPlan fresh;
-      if (int rc = make_plan(fresh, rows, k, n, ld_x, ld_res, ld_out, dtype, bias != nullptr, (size_t)workspace_bytes)) return rc;
+      if (int rc = make_plan(fresh, rows, k, n, ld_x, ld_res, ld_out, dtype, bias != nullptr, (size_t)workspace_bytes, batch)) return rc;
       it = g_plans.emplace(key, fresh).first;
     }
     plan = it->second;
@@ -107,6 +126,7 @@ extern "C" int vf_linear_residual(const void* x, const void* w, const void* bias
     if (ld_out != ld_res) {
       const cudaDataType_t dt = dtype == VF_BF16 ? CUDA_R_16BF : CUDA_R_32F;
       VF_LT_TRY(cublasLtMatrixLayoutCreate(&d_own, dt, (uint64_t)n, (uint64_t)rows, (int64_t)ld_out));
+      if (batch > 1) if (int rc = set_batch(d_own, batch, rows * ld_out)) return rc;
       d = d_own;
     }
     cublasStatus_t s = cublasLtMatmul(g_lt, plan.op, &alpha, w, plan.a, x, plan.b, &beta, residual, plan.c, out, d, &plan.algo,
@@ -115,4 +135,17 @@ extern "C" int vf_linear_residual(const void* x, const void* w, const void* bias
     if (s != CUBLAS_STATUS_SUCCESS) return lt_fail(s, "cublasLtMatmul");
   }
   return 0;
+}
+
+extern "C" int vf_linear_residual(const void* x, const void* w, const void* bias, const void* residual, void* out,
+                                  long long rows, int k, int n, long long ld_x, long long ld_res, long long ld_out,
+                                  void* workspace, long long workspace_bytes, int dtype, void* stream) {
+  return linear_residual_impl(x, w, bias, residual, out, 1, rows, k, n, ld_x, ld_res, ld_out, workspace, workspace_bytes, dtype, stream);
+}
+
+// Per-sample bias: x, residual, out are (batch, rows, .) contiguous per sample, bias is (batch, n).
+extern "C" int vf_linear_residual_batched(const void* x, const void* w, const void* bias, const void* residual, void* out,
+                                          int batch, long long rows, int k, int n, long long ld_x, long long ld_res,
+                                          long long ld_out, void* workspace, long long workspace_bytes, int dtype, void* stream) {
+  return linear_residual_impl(x, w, bias, residual, out, batch, rows, k, n, ld_x, ld_res, ld_out, workspace, workspace_bytes, dtype, stream);
 }

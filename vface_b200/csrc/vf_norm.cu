@@ -527,76 +527,159 @@ struct LnParams {
   float eps;
 };
 
-template <typename T, int MAXC>   // MAXC: 16-byte chunks per lane
+// R rows per warp, all of their loads issued before the first reduction: one row per warp (640 B at c = 320) left
+// an SM with 41 KB in flight and the single-input form at 44 % of HBM.
+template <typename T, int MAXC, int R>   // MAXC: 16-byte chunks per lane
 __global__ void __launch_bounds__(kLnWarps * 32)
 add_layer_norm_kernel(const LnParams P) {
   constexpr int E = V16<T>::E;
   const int lane = threadIdx.x & 31;
-  const long long row = (long long)blockIdx.x * kLnWarps + (threadIdx.x >> 5);
-  if (row >= P.rows) return;
+  const long long row0 = ((long long)blockIdx.x * kLnWarps + (threadIdx.x >> 5)) * R;
+  if (row0 >= P.rows) return;
   const int chunks = P.c / E;
-  const T* x = reinterpret_cast<const T*>(P.x) + row * P.c;
-  const T* y = P.y ? reinterpret_cast<const T*>(P.y) + row * P.c : nullptr;
-  const T* bias = nullptr;
-  if (P.bias) bias = reinterpret_cast<const T*>(P.bias) + (P.rows_per_bias > 0 ? (row / P.rows_per_bias) * P.c : 0);
-  float v[MAXC][E];
-  float s = 0.f;
+  float v[R][MAXC][E];
+  float s[R];
 #pragma unroll
-  for (int k = 0; k < MAXC; ++k) {
-    const int ch = lane + 32 * k;
-    if (ch < chunks) {
-      V16<T>::ld(x + ch * E, v[k]);
-      if (y) {
-        float t[E];
-        V16<T>::ld(y + ch * E, t);
+  for (int r = 0; r < R; ++r) {
+    const long long row = row0 + r;
+    s[r] = 0.f;
+    if (row >= P.rows) continue;
+    const T* x = reinterpret_cast<const T*>(P.x) + row * P.c;
+    const T* y = P.y ? reinterpret_cast<const T*>(P.y) + row * P.c : nullptr;
+    const T* bias = nullptr;
+    if (P.bias) bias = reinterpret_cast<const T*>(P.bias) + (P.rows_per_bias > 0 ? (row / P.rows_per_bias) * P.c : 0);
 #pragma unroll
-        for (int j = 0; j < E; ++j) v[k][j] += t[j];
-      }
-      if (bias) {
-        float t[E];
-        V16<T>::ld(bias + ch * E, t);
+    for (int k = 0; k < MAXC; ++k) {
+      const int ch = lane + 32 * k;
+      if (ch < chunks) {
+        V16<T>::ld(x + ch * E, v[r][k]);
+        if (y) {
+          float t[E];
+          V16<T>::ld(y + ch * E, t);
 #pragma unroll
-        for (int j = 0; j < E; ++j) v[k][j] += t[j];
-      }
-      if (P.res) {
-        // the residual stream is stored in T; normalise what was stored so both consumers agree
-        V16<T>::st(reinterpret_cast<T*>(P.res) + row * P.c + ch * E, v[k]);
-        if (sizeof(T) == 2) {
-#pragma unroll
-          for (int j = 0; j < E; ++j) v[k][j] = __bfloat162float(__float2bfloat16_rn(v[k][j]));
+          for (int j = 0; j < E; ++j) v[r][k][j] += t[j];
         }
+        if (bias) {
+          float t[E];
+          V16<T>::ld(bias + ch * E, t);
+#pragma unroll
+          for (int j = 0; j < E; ++j) v[r][k][j] += t[j];
+        }
+        if (P.res) {
+          // the residual stream is stored in T; normalise what was stored so both consumers agree
+          V16<T>::st(reinterpret_cast<T*>(P.res) + row * P.c + ch * E, v[r][k]);
+          if (sizeof(T) == 2) {
+#pragma unroll
+            for (int j = 0; j < E; ++j) v[r][k][j] = __bfloat162float(__float2bfloat16_rn(v[r][k][j]));
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < E; ++j) s[r] += v[r][k][j];
       }
-#pragma unroll
-      for (int j = 0; j < E; ++j) s += v[k][j];
     }
   }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  const float mean = s / (float)P.c;
-  float q = 0.f;
-#pragma unroll
-  for (int k = 0; k < MAXC; ++k) {
-    if (lane + 32 * k < chunks) {
-#pragma unroll
-      for (int j = 0; j < E; ++j) { const float t = v[k][j] - mean; q = fmaf(t, t, q); }
-    }
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
-  const float rstd = rsqrtf(q / (float)P.c + P.eps);
   const T* gamma = reinterpret_cast<const T*>(P.gamma);
   const T* beta = reinterpret_cast<const T*>(P.beta);
-  T* out = reinterpret_cast<T*>(P.out) + row * P.c;
 #pragma unroll
-  for (int k = 0; k < MAXC; ++k) {
-    const int ch = lane + 32 * k;
-    if (ch < chunks) {
-      float g[E], b[E];
-      V16<T>::ld(gamma + ch * E, g);
-      V16<T>::ld(beta + ch * E, b);
+  for (int r = 0; r < R; ++r) {
+    const long long row = row0 + r;
+    if (row >= P.rows) continue;                       // warp-uniform
+    float sum = s[r];
 #pragma unroll
-      for (int j = 0; j < E; ++j) v[k][j] = fmaf((v[k][j] - mean) * rstd, g[j], b[j]);
-      V16<T>::st(out + ch * E, v[k]);
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float mean = sum / (float)P.c;
+    float q = 0.f;
+#pragma unroll
+    for (int k = 0; k < MAXC; ++k) {
+      if (lane + 32 * k < chunks) {
+#pragma unroll
+        for (int j = 0; j < E; ++j) { const float t = v[r][k][j] - mean; q = fmaf(t, t, q); }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    const float rstd = rsqrtf(q / (float)P.c + P.eps);
+    T* out = reinterpret_cast<T*>(P.out) + row * P.c;
+#pragma unroll
+    for (int k = 0; k < MAXC; ++k) {
+      const int ch = lane + 32 * k;
+      if (ch < chunks) {
+        float g[E], b[E];
+        V16<T>::ld(gamma + ch * E, g);
+        V16<T>::ld(beta + ch * E, b);
+#pragma unroll
+        for (int j = 0; j < E; ++j) v[r][k][j] = fmaf((v[r][k][j] - mean) * rstd, g[j], b[j]);
+        V16<T>::st(out + ch * E, v[r][k]);
+      }
+    }
+  }
+}
+
+// Pure LayerNorm (no add, nothing to store back): the rows stay PACKED in registers (4 per 16-byte chunk instead of
+// 8 floats), so R = 4 rows per warp cost ~60 registers and four CTAs stay resident: ~80 KB of loads in flight per SM.
+template <typename T, int MAXC, int R>
+__global__ void __launch_bounds__(kLnWarps * 32, MAXC <= 2 ? 4 : 3)
+layer_norm_kernel(const LnParams P) {
+  constexpr int E = V16<T>::E;
+  const int lane = threadIdx.x & 31;
+  const long long row0 = ((long long)blockIdx.x * kLnWarps + (threadIdx.x >> 5)) * R;
+  if (row0 >= P.rows) return;
+  const int chunks = P.c / E;
+  uint4 raw[R][MAXC];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const long long row = row0 + r < P.rows ? row0 + r : P.rows - 1;      // clamp: tail rows are recomputed, not stored
+    const T* x = reinterpret_cast<const T*>(P.x) + row * P.c;
+#pragma unroll
+    for (int k = 0; k < MAXC; ++k) {
+      const int ch = lane + 32 * k;
+      raw[r][k] = ch < chunks ? ld_nc_v4(x + ch * E) : make_uint4(0u, 0u, 0u, 0u);
+    }
+  }
+  const T* gamma = reinterpret_cast<const T*>(P.gamma);
+  const T* beta = reinterpret_cast<const T*>(P.beta);
+  const float inv_c = 1.0f / (float)P.c;
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const long long row = row0 + r;
+    if (row >= P.rows) break;                          // warp-uniform
+    float sum = 0.f;
+#pragma unroll
+    for (int k = 0; k < MAXC; ++k) {
+      float v[E];
+      V16<T>::unpack(raw[r][k], v);                    // padding chunks are zero
+#pragma unroll
+      for (int j = 0; j < E; ++j) sum += v[j];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float mean = sum * inv_c;
+    float q = 0.f;
+#pragma unroll
+    for (int k = 0; k < MAXC; ++k) {
+      if (lane + 32 * k < chunks) {
+        float v[E];
+        V16<T>::unpack(raw[r][k], v);
+#pragma unroll
+        for (int j = 0; j < E; ++j) { const float t = v[j] - mean; q = fmaf(t, t, q); }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    const float rstd = rsqrtf(q * inv_c + P.eps);
+    T* out = reinterpret_cast<T*>(P.out) + row * P.c;
+#pragma unroll
+    for (int k = 0; k < MAXC; ++k) {
+      const int ch = lane + 32 * k;
+      if (ch < chunks) {
+        float v[E], g[E], b[E];
+        V16<T>::unpack(raw[r][k], v);
+        V16<T>::ld(gamma + ch * E, g);
+        V16<T>::ld(beta + ch * E, b);
+#pragma unroll
+        for (int j = 0; j < E; ++j) v[j] = fmaf((v[j] - mean) * rstd, g[j], b[j]);
+        st_na_v4(out + ch * E, V16<T>::pack(v));
+      }
     }
   }
 }
@@ -843,15 +926,21 @@ extern "C" int vf_add_layer_norm(const void* x, const void* y, const void* bias,
   LnParams P;
   P.x = x; P.y = y; P.bias = bias; P.gamma = gamma; P.beta = beta; P.res = res; P.out = out;
   P.rows = rows; P.rows_per_bias = rows_per_bias; P.c = c; P.eps = eps;
-  const long long blocks = (rows + kLnWarps - 1) / kLnWarps;
+  const bool pure = !y && !bias && !res;
+  // rows per warp: only the pure form (packed registers) gains from several rows in flight; with the add the extra
+  // registers cost more occupancy than the rows bring (measured 0.24 -> 0.43 ms at c = 320), so it stays at one
+  const int rpw = !pure ? 1 : per_lane <= 2 ? 4 : per_lane <= 5 ? 2 : 1;
+  const long long blocks = (rows + (long long)kLnWarps * rpw - 1) / ((long long)kLnWarps * rpw);
   if (blocks > 2147483647LL) return fail("vf_add_layer_norm: too many rows");
   cudaStream_t st = (cudaStream_t)stream;
   const int thr = kLnWarps * 32;
-#define VF_LN_LAUNCH(T)                                                                   \
-  do {                                                                                    \
-    if (per_lane <= 2) add_layer_norm_kernel<T, 2><<<(int)blocks, thr, 0, st>>>(P);        \
-    else if (per_lane <= 5) add_layer_norm_kernel<T, 5><<<(int)blocks, thr, 0, st>>>(P);   \
-    else add_layer_norm_kernel<T, 10><<<(int)blocks, thr, 0, st>>>(P);                     \
+#define VF_LN_LAUNCH(T)                                                                      \
+  do {                                                                                       \
+    if (pure && per_lane <= 2) layer_norm_kernel<T, 2, 4><<<(int)blocks, thr, 0, st>>>(P);    \
+    else if (pure && per_lane <= 5) layer_norm_kernel<T, 5, 2><<<(int)blocks, thr, 0, st>>>(P); \
+    else if (per_lane <= 2) add_layer_norm_kernel<T, 2, 1><<<(int)blocks, thr, 0, st>>>(P);   \
+    else if (per_lane <= 5) add_layer_norm_kernel<T, 5, 1><<<(int)blocks, thr, 0, st>>>(P);   \
+    else add_layer_norm_kernel<T, 10, 1><<<(int)blocks, thr, 0, st>>>(P);                     \
   } while (0)
   if (dtype == VF_F32) VF_LN_LAUNCH(float); else VF_LN_LAUNCH(__nv_bfloat16);
 #undef VF_LN_LAUNCH

@@ -107,7 +107,7 @@ def register_spa_attn_injection(model, injection_schedule, switch_on=True, input
                                              f"{' + halo' if halo_q is not None else ''}; expected {want}")
                         ops.flow_warp_blend(sq, flow, alpha, FLOW_HW, FLOW_HW, prev_halo=halo_q, out=cond_q)
                         ops.flow_warp_blend(sk, flow, alpha, FLOW_HW, FLOW_HW, prev_halo=halo_k, out=cond_k)
-            return self.to_out(self.attend(q, k, v))
+            return self.project_out(self.attend(q, k, v))
 
         return forward
 

@@ -105,6 +105,18 @@ class CrossAttention(nn.Module):
         """softmax(q k^T * scale) v, heads indexed inside the kernel (reference :270-286 / :206-220)."""
         return ops.attention(q, k, v, self.heads, self.scale)
 
+    def project_out(self, a):
+        """to_out(a) (reference :221 / pnp_utils.py:287).  When the enclosing BasicTransformerBlock has armed
+        `_fused_out` (bf16, single-token context), the projection, its bias, attn2's per-sample row and the residual add
+        are ONE library GEMM and the result is the updated residual stream; `_fused_out.done` tells the block so.
+        A foreign `forward` that calls `self.to_out` directly simply leaves it unarmed-and-undone."""
+        ep = getattr(self, "_fused_out", None)
+        if ep is not None and not ep.done and a.dtype == torch.bfloat16 and a.dim() == 3 and a.shape[1] >= 256:
+            lin = self.to_out[0]
+            ep.done = True
+            return ops.linear_residual(a.contiguous(), lin.weight, (lin.bias + ep.row).contiguous(), ep.residual)
+        return self.to_out(a)
+
     def single_token_row(self, context):
         """Cross-attention against ONE context token: softmax over one key == 1 exactly, so every query
         gets to_out(to_v(context)) -- (b, 1, query_dim), independent of x."""
@@ -115,7 +127,7 @@ class CrossAttention(nn.Module):
             raise NotImplementedError("attention masks are not used on the VFace hot path")
         if context is None:
             q, k, v = self.project_qkv(x)
-            return self.to_out(self.attend(q, k, v))
+            return self.project_out(self.attend(q, k, v))
         if context.shape[-1] == 768 * 2:
             raise NotImplementedError("split clip/landmark contexts (1536-wide) are not used by the VFace configuration")
         if context.shape[1] == 1:
@@ -124,6 +136,18 @@ class CrossAttention(nn.Module):
         k = self.to_k(context)
         v = self.to_v(context)
         return self.to_out(self.attend(q, k, v))
+
+
+import os as _os
+_FUSE_TO_OUT = _os.environ.get("VF_FUSE_TO_OUT", "1") != "0"     # tuning knob: 0 keeps to_out and the LN3 add separate
+
+
+class _FusedOut:
+    """Epilogue armed by BasicTransformerBlock around its attn1 call (see CrossAttention.project_out)."""
+    __slots__ = ("residual", "row", "done")
+
+    def __init__(self, residual, row):
+        self.residual, self.row, self.done = residual, row, False
 
 
 class BasicTransformerBlock(nn.Module):
@@ -149,17 +173,29 @@ class BasicTransformerBlock(nn.Module):
         # module.forward (ldm/models/pnp_utils.py:289-339), take effect exactly as in the reference.
         x = x.contiguous()
         ln = lambda m, t, **kw: ops.add_layer_norm(t, m.weight, m.bias, m.eps, **kw)
-        a1 = self.attn1(ln(self.norm1, x))
         single = (context is not None and context.shape[1] == 1 and context.shape[-1] != 768 * 2
                   and "forward" not in self.attn2.__dict__)
         if single:
-            # attn2's output does not depend on its queries: LN2 is dead, both adds fold into LN3
+            # attn2's output does not depend on its queries: LN2 is dead and both adds fold into one pass.  bf16: that
+            # pass is the to_out GEMM of attn1 itself (x + to_out(a) + b + row in its epilogue, one rounding of the
+            # stream); otherwise the LN3 kernel adds a1 and the row while it normalises.
             row = self.attn2.single_token_row(context)[:, 0]
-            x, n3 = ln(self.norm3, x, y=a1.contiguous(), row_bias=row)
-        else:
-            x, n2 = ln(self.norm2, x, y=a1.contiguous())
-            a2 = self.attn2(n2, context=context)
-            x, n3 = ln(self.norm3, x, y=a2.contiguous())
+            ep = _FusedOut(x, row) if (x.dtype == torch.bfloat16 and _FUSE_TO_OUT) else None
+            self.attn1._fused_out = ep
+            try:
+                a1 = self.attn1(ln(self.norm1, x))
+            finally:
+                self.attn1._fused_out = None
+            if ep is not None and ep.done:
+                x = a1                                      # already x + attn1 + attn2
+                n3 = ln(self.norm3, x)
+            else:
+                x, n3 = ln(self.norm3, x, y=a1.contiguous(), row_bias=row)
+            return self._ff_residual(x, n3)
+        a1 = self.attn1(ln(self.norm1, x))
+        x, n2 = ln(self.norm2, x, y=a1.contiguous())
+        a2 = self.attn2(n2, context=context)
+        x, n3 = ln(self.norm3, x, y=a2.contiguous())
         return self._ff_residual(x, n3)
 
     def _ff_residual(self, x, n3):

@@ -108,6 +108,17 @@ class ResBlock(TimestepBlock):
     def forward(self, x, emb):
         return self._forward(x, emb)
 
+    def _split_skip_weight(self, c1):
+        """The 1x1 skip convolution's weight as two contiguous (out, c1) / (out, c - c1) matrices (the two sources of a
+        never-materialised channel concatenation), cached until the parameter changes."""
+        wp = self.skip_connection.weight
+        key = (wp.data_ptr(), wp._version, wp.dtype, wp.device, c1)
+        if getattr(self, "_skip_split_key", None) != key:
+            w = wp.detach().reshape(self.out_channels, self.channels)
+            self._skip_split = (w[:, :c1].contiguous(), w[:, c1:].contiguous())
+            self._skip_split_key = key
+        return self._skip_split
+
     def _forward(self, x, emb):
         """GN-SiLU-conv, + emb, GN-SiLU-conv, + skip (reference :255-275) on channels-last activations:
         the two GroupNorm+SiLU are one fused kernel each, the `+ emb_out` and the first conv bias ride
@@ -129,20 +140,29 @@ class ResBlock(TimestepBlock):
                                  silu=True, add_nc=add)
         h2 = F.conv2d(g2.permute(0, 3, 1, 2), conv2.weight, None, padding=1).permute(0, 2, 3, 1).contiguous()
         bias = conv2.bias
+        fuse = h2.dtype == torch.bfloat16       # bf16: 1x1 skip convolution + biases + residual in the library GEMM's epilogue
+        rows = n * hh * ww
         if x2t is not None:
             if isinstance(self.skip_connection, nn.Identity) or self.skip_connection.kernel_size != (1, 1):
                 raise NotImplementedError("a concatenated ResBlock input needs the 1x1 skip convolution")
-            w = self.skip_connection.weight.reshape(self.out_channels, self.channels)
-            rows = n * hh * ww
-            skip = torch.mm(xt.reshape(rows, c), w[:, :c].t())
-            skip.addmm_(x2t.reshape(rows, self.channels - c), w[:, c:].t())
-            skip = skip.reshape(n, hh, ww, self.out_channels)
             bias = bias + self.skip_connection.bias
+            w1, w2 = self._split_skip_weight(c)
+            if fuse:
+                out = ops.linear_residual(xt.reshape(rows, c), w1, bias, h2.reshape(rows, self.out_channels))
+                out = ops.linear_residual(x2t.reshape(rows, self.channels - c), w2, None, out)
+                return out.reshape(n, hh, ww, self.out_channels).permute(0, 3, 1, 2)
+            skip = torch.mm(xt.reshape(rows, c), w1.t())
+            skip.addmm_(x2t.reshape(rows, self.channels - c), w2.t())
+            skip = skip.reshape(n, hh, ww, self.out_channels)
         elif isinstance(self.skip_connection, nn.Identity):
             skip = xt
         elif self.skip_connection.kernel_size == (1, 1):
-            skip = F.linear(xt, self.skip_connection.weight.reshape(self.out_channels, c))
             bias = bias + self.skip_connection.bias
+            w = self.skip_connection.weight.reshape(self.out_channels, c)
+            if fuse and w.is_contiguous():
+                out = ops.linear_residual(xt.reshape(rows, c), w, bias, h2.reshape(rows, self.out_channels))
+                return out.reshape(n, hh, ww, self.out_channels).permute(0, 3, 1, 2)
+            skip = F.linear(xt, w)
         else:
             skip = self.skip_connection(x).permute(0, 2, 3, 1).contiguous()
         out = ops.add_bias(skip, h2, bias)

@@ -397,7 +397,8 @@ _lt_workspace = {}
 def linear_residual(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], residual: torch.Tensor) -> torch.Tensor:
     """residual + x @ weight^T + bias in ONE library GEMM (cuBLASLt: beta = 1 and the bias in the fp32 epilogue), for
     `x = ff(norm3(x)) + x` (attention.py:242) and `proj_out(x) + x_in` (attention.py:287-288): the projection is never
-    rounded and written out just to be re-read by an add.  Returns a new tensor; `residual` is not modified."""
+    rounded and written out just to be re-read by an add.  Returns a new tensor; `residual` is not modified.
+    bias may be (n,) or, for x of shape (batch, rows, k), one row per batch entry: (batch, n)."""
     _need_cuda(x, weight, bias, residual)
     n, k = weight.shape
     if x.shape[-1] != k or residual.shape[-1] != n or x.shape[:-1] != residual.shape[:-1]:
@@ -410,8 +411,17 @@ def linear_residual(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.
     ws = _lt_workspace.get(x.device)
     if ws is None:
         ws = _lt_workspace[x.device] = torch.empty(32 << 20, dtype=torch.uint8, device=x.device)
-    rows = x.numel() // k
     lib = _lib.load()
+    if bias is not None and bias.dim() == 2:
+        if x.dim() != 3 or bias.shape != (x.shape[0], n) or not bias.is_contiguous():
+            raise ValueError("linear_residual: a per-batch bias needs x (batch, rows, k) and bias (batch, n)")
+        rc = lib.vf_linear_residual_batched(x.data_ptr(), weight.data_ptr(), bias.data_ptr(), residual.data_ptr(), out.data_ptr(),
+                                            x.shape[0], x.shape[1], k, n, k, n, n, ws.data_ptr(), ws.numel(), _code(x), _stream(x))
+        _lib.check(rc, "vf_linear_residual_batched")
+        return out
+    if bias is not None and (bias.numel() != n or not bias.is_contiguous()):
+        raise ValueError("linear_residual: bad bias")
+    rows = x.numel() // k
     rc = lib.vf_linear_residual(x.data_ptr(), weight.data_ptr(), bias.data_ptr() if bias is not None else None,
                                 residual.data_ptr(), out.data_ptr(), rows, k, n, k, n, n, ws.data_ptr(), ws.numel(),
                                 _code(x), _stream(x))
