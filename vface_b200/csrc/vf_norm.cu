@@ -280,7 +280,12 @@ gn_apply_kernel(const GnParams P) {
 }
 
 static void gn_plan(int n, int hw, int* slabs, int* rows_per_slab) {
-  int want = (4 * num_sms() + n - 1) / n;
+  // CTAs per SM the (slabs x samples) grid aims for.  Swept 4..24 on B200 (VF_GN_CTAS_PER_SM): 6 is the best at every
+  // level of the UNet (64x64x320: 64 -> 73 % of HBM; cat(320+320): 62 -> 74 %): 4 leaves a partial second wave of
+  // fat CTAs, 16+ pays per-CTA prologue and statistics reduction.
+  static int per_sm = -1;
+  if (per_sm < 0) { const char* e_ = getenv("VF_GN_CTAS_PER_SM"); per_sm = e_ ? atoi(e_) : 6; if (per_sm < 1) per_sm = 6; }
+  int want = (per_sm * num_sms() + n - 1) / n;
   if (want < 1) want = 1;
   if (want > 64) want = 64;
   int rps = (hw + want - 1) / want;
