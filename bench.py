@@ -241,6 +241,7 @@ def main():
     device = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # NCCL's version banner must not share stdout with the JSON line
         dist.init_process_group("nccl", device_id=device)
     W = max(args.warmup, 3)
     K = max(args.steps, 1)
