@@ -352,10 +352,17 @@ def main():
                 traffic = json.load(open(tp)).get("dram_bytes_per_launch")
             except Exception:
                 traffic = None
-        roof = dict(bound="tensor", kernel="vf::attn_tc_kernel<BN=64, S/O 128 + P 32 TMEM cols, 3 CTAs/SM> (N=4096, 8 heads x d40)", achieved=ach,
+        # what the hardware allows at d = 40: one MUFU.EX2 per 160 MMA flops, 15.9 MUFU.EX2/clk/SM measured
+        # (experiments/mufu_rate.cu), at the SM clock sampled during the timed steps
+        sm_mhz = (clock_info or {}).get("sm_mhz") or pk.get("sm_max_mhz") or 1965.0
+        n_sm = torch.cuda.get_device_properties(device).multi_processor_count
+        mufu_ceiling = n_sm * 15.9 * sm_mhz * 1e6 * 160.0 / 1e12
+        roof = dict(bound="tensor", kernel="vf::attn_tc_kernel<BN=64, S/O 128 + P 32 TMEM cols, 3 CTAs/SM, 2 MMA issuer warps> (N=4096, 8 heads x d40)", achieved=ach,
                     peak=pk["tc_sustained"], unit="TFLOP/s", frac=ach / pk["tc_sustained"], traffic=traffic,
                     peak_source=f"{pk['src']} sustained bf16 (kernel timed inside a long step); burst {pk['tc_burst']}",
                     frac_of_burst=ach / pk["tc_burst"], launches_timed=len(attn_ms), avg_launch_ms=avg_ms,
+                    mufu_ex2_ceiling_tflops=mufu_ceiling, frac_of_mufu_ex2_ceiling=ach / mufu_ceiling,
+                    ceiling_note="d_head 40: one exponential per 160 MMA flops; ceiling = SMs x 15.9 MUFU.EX2/clk x sampled SM clock x 160",
                     share_of_step=float(np.sum(attn_ms)) / K / ms_per_step,
                     algorithmic_flops_per_launch=flops)
 
