@@ -11,11 +11,57 @@
 #include "vf_common.cuh"
 
 #include <cublasLt.h>
+#include <dlfcn.h>
 #include <map>
 #include <mutex>
 #include <tuple>
 
 namespace vf {
+
+// cuBLASLt is bound at RUN time, not link time: the host process (PyTorch) ships its own libcublas / libcublasLt
+// pair, and a DT_NEEDED entry here would let the dynamic loader pull the SYSTEM libcublasLt in first whenever this
+// library is loaded before torch -- torch's libcublas 12.8 then runs against a 12.9 libcublasLt and its first
+// cublasGemmEx fails with CUBLAS_STATUS_INVALID_VALUE (seen in __graft_entry__: build() then smoke() in one
+// process).  So: take the copy that is already loaded (RTLD_NOLOAD), and only load one ourselves if there is none.
+struct LtApi {
+  decltype(&cublasLtCreate) Create;
+  decltype(&cublasLtMatmulDescCreate) MatmulDescCreate;
+  decltype(&cublasLtMatmulDescSetAttribute) MatmulDescSetAttribute;
+  decltype(&cublasLtMatrixLayoutCreate) MatrixLayoutCreate;
+  decltype(&cublasLtMatrixLayoutSetAttribute) MatrixLayoutSetAttribute;
+  decltype(&cublasLtMatrixLayoutDestroy) MatrixLayoutDestroy;
+  decltype(&cublasLtMatmulPreferenceCreate) MatmulPreferenceCreate;
+  decltype(&cublasLtMatmulPreferenceSetAttribute) MatmulPreferenceSetAttribute;
+  decltype(&cublasLtMatmulPreferenceDestroy) MatmulPreferenceDestroy;
+  decltype(&cublasLtMatmulAlgoGetHeuristic) MatmulAlgoGetHeuristic;
+  decltype(&cublasLtMatmul) Matmul;
+  bool ok = false;
+};
+static LtApi g_api;
+
+static int load_lt_api() {           // call with g_lt_mutex held
+  if (g_api.ok) return 0;
+  void* h = dlopen("libcublasLt.so.12", RTLD_NOW | RTLD_NOLOAD);
+  if (!h) h = dlopen("libcublasLt.so.12", RTLD_NOW | RTLD_LOCAL);
+  if (!h) return fail("vf_linear_residual: libcublasLt.so.12 is not loaded and cannot be loaded (%s)", dlerror());
+#define VF_LT_SYM(field, name)                                                            \
+  g_api.field = reinterpret_cast<decltype(g_api.field)>(dlsym(h, #name));                 \
+  if (!g_api.field) return fail("vf_linear_residual: symbol %s not found in libcublasLt.so.12", #name);
+  VF_LT_SYM(Create, cublasLtCreate)
+  VF_LT_SYM(MatmulDescCreate, cublasLtMatmulDescCreate)
+  VF_LT_SYM(MatmulDescSetAttribute, cublasLtMatmulDescSetAttribute)
+  VF_LT_SYM(MatrixLayoutCreate, cublasLtMatrixLayoutCreate)
+  VF_LT_SYM(MatrixLayoutSetAttribute, cublasLtMatrixLayoutSetAttribute)
+  VF_LT_SYM(MatrixLayoutDestroy, cublasLtMatrixLayoutDestroy)
+  VF_LT_SYM(MatmulPreferenceCreate, cublasLtMatmulPreferenceCreate)
+  VF_LT_SYM(MatmulPreferenceSetAttribute, cublasLtMatmulPreferenceSetAttribute)
+  VF_LT_SYM(MatmulPreferenceDestroy, cublasLtMatmulPreferenceDestroy)
+  VF_LT_SYM(MatmulAlgoGetHeuristic, cublasLtMatmulAlgoGetHeuristic)
+  VF_LT_SYM(Matmul, cublasLtMatmul)
+#undef VF_LT_SYM
+  g_api.ok = true;
+  return 0;
+}
 
 struct LtPlan {
   cublasLtMatmulDesc_t op = nullptr;
@@ -39,8 +85,8 @@ static int lt_fail(cublasStatus_t s, const char* what) { return fail("vf_linear_
 static int set_batch(cublasLtMatrixLayout_t l, int batch, long long stride) {
   const int32_t b = batch;
   const int64_t st = stride;
-  VF_LT_TRY(cublasLtMatrixLayoutSetAttribute(l, CUBLASLT_MATRIX_LAYOUT_BATCH_COUNT, &b, sizeof(b)));
-  VF_LT_TRY(cublasLtMatrixLayoutSetAttribute(l, CUBLASLT_MATRIX_LAYOUT_STRIDED_BATCH_OFFSET, &st, sizeof(st)));
+  VF_LT_TRY(g_api.MatrixLayoutSetAttribute(l, CUBLASLT_MATRIX_LAYOUT_BATCH_COUNT, &b, sizeof(b)));
+  VF_LT_TRY(g_api.MatrixLayoutSetAttribute(l, CUBLASLT_MATRIX_LAYOUT_STRIDED_BATCH_OFFSET, &st, sizeof(st)));
   return 0;
 }
 
@@ -48,21 +94,21 @@ static int set_batch(cublasLtMatrixLayout_t l, int batch, long long stride) {
 static int make_plan(LtPlan& P, long long rows, int k, int n, long long ld_x, long long ld_res, long long ld_out, int dtype,
                      bool has_bias, size_t ws_bytes, int batch) {
   const cudaDataType_t dt = dtype == VF_BF16 ? CUDA_R_16BF : CUDA_R_32F;
-  VF_LT_TRY(cublasLtMatmulDescCreate(&P.op, CUBLAS_COMPUTE_32F, CUDA_R_32F));
+  VF_LT_TRY(g_api.MatmulDescCreate(&P.op, CUBLAS_COMPUTE_32F, CUDA_R_32F));
   // row-major out (rows, n) = x (rows, k) . W^T  <=>  column-major out^T (n, rows) = W (k, n)^T . x^T (k, rows)
   const cublasOperation_t ta = CUBLAS_OP_T, tb = CUBLAS_OP_N;
-  VF_LT_TRY(cublasLtMatmulDescSetAttribute(P.op, CUBLASLT_MATMUL_DESC_TRANSA, &ta, sizeof(ta)));
-  VF_LT_TRY(cublasLtMatmulDescSetAttribute(P.op, CUBLASLT_MATMUL_DESC_TRANSB, &tb, sizeof(tb)));
+  VF_LT_TRY(g_api.MatmulDescSetAttribute(P.op, CUBLASLT_MATMUL_DESC_TRANSA, &ta, sizeof(ta)));
+  VF_LT_TRY(g_api.MatmulDescSetAttribute(P.op, CUBLASLT_MATMUL_DESC_TRANSB, &tb, sizeof(tb)));
   if (has_bias) {
     const cublasLtEpilogue_t ep = CUBLASLT_EPILOGUE_BIAS;
-    VF_LT_TRY(cublasLtMatmulDescSetAttribute(P.op, CUBLASLT_MATMUL_DESC_EPILOGUE, &ep, sizeof(ep)));
-    VF_LT_TRY(cublasLtMatmulDescSetAttribute(P.op, CUBLASLT_MATMUL_DESC_BIAS_DATA_TYPE, &dt, sizeof(dt)));
+    VF_LT_TRY(g_api.MatmulDescSetAttribute(P.op, CUBLASLT_MATMUL_DESC_EPILOGUE, &ep, sizeof(ep)));
+    VF_LT_TRY(g_api.MatmulDescSetAttribute(P.op, CUBLASLT_MATMUL_DESC_BIAS_DATA_TYPE, &dt, sizeof(dt)));
   }
-  VF_LT_TRY(cublasLtMatrixLayoutCreate(&P.a, dt, (uint64_t)k, (uint64_t)n, (int64_t)k));
-  VF_LT_TRY(cublasLtMatrixLayoutCreate(&P.b, dt, (uint64_t)k, (uint64_t)rows, (int64_t)ld_x));
-  VF_LT_TRY(cublasLtMatrixLayoutCreate(&P.c, dt, (uint64_t)n, (uint64_t)rows, (int64_t)ld_res));
+  VF_LT_TRY(g_api.MatrixLayoutCreate(&P.a, dt, (uint64_t)k, (uint64_t)n, (int64_t)k));
+  VF_LT_TRY(g_api.MatrixLayoutCreate(&P.b, dt, (uint64_t)k, (uint64_t)rows, (int64_t)ld_x));
+  VF_LT_TRY(g_api.MatrixLayoutCreate(&P.c, dt, (uint64_t)n, (uint64_t)rows, (int64_t)ld_res));
   cublasLtMatrixLayout_t d = nullptr;
-  VF_LT_TRY(cublasLtMatrixLayoutCreate(&d, dt, (uint64_t)n, (uint64_t)rows, (int64_t)ld_out));
+  VF_LT_TRY(g_api.MatrixLayoutCreate(&d, dt, (uint64_t)n, (uint64_t)rows, (int64_t)ld_out));
   if (batch > 1) {
     if (int rc = set_batch(P.a, batch, 0)) return rc;
     if (int rc = set_batch(P.b, batch, rows * ld_x)) return rc;
@@ -70,17 +116,17 @@ static int make_plan(LtPlan& P, long long rows, int k, int n, long long ld_x, lo
     if (int rc = set_batch(d, batch, rows * ld_out)) return rc;
     if (has_bias) {
       const int64_t bs = n;
-      VF_LT_TRY(cublasLtMatmulDescSetAttribute(P.op, CUBLASLT_MATMUL_DESC_BIAS_BATCH_STRIDE, &bs, sizeof(bs)));
+      VF_LT_TRY(g_api.MatmulDescSetAttribute(P.op, CUBLASLT_MATMUL_DESC_BIAS_BATCH_STRIDE, &bs, sizeof(bs)));
     }
   }
   cublasLtMatmulPreference_t pref = nullptr;
-  VF_LT_TRY(cublasLtMatmulPreferenceCreate(&pref));
-  VF_LT_TRY(cublasLtMatmulPreferenceSetAttribute(pref, CUBLASLT_MATMUL_PREF_MAX_WORKSPACE_BYTES, &ws_bytes, sizeof(ws_bytes)));
+  VF_LT_TRY(g_api.MatmulPreferenceCreate(&pref));
+  VF_LT_TRY(g_api.MatmulPreferenceSetAttribute(pref, CUBLASLT_MATMUL_PREF_MAX_WORKSPACE_BYTES, &ws_bytes, sizeof(ws_bytes)));
   cublasLtMatmulHeuristicResult_t res;
   int found = 0;
-  cublasStatus_t s = cublasLtMatmulAlgoGetHeuristic(g_lt, P.op, P.a, P.b, P.c, d, pref, 1, &res, &found);
-  cublasLtMatmulPreferenceDestroy(pref);
-  cublasLtMatrixLayoutDestroy(d);
+  cublasStatus_t s = g_api.MatmulAlgoGetHeuristic(g_lt, P.op, P.a, P.b, P.c, d, pref, 1, &res, &found);
+  g_api.MatmulPreferenceDestroy(pref);
+  g_api.MatrixLayoutDestroy(d);
   if (s != CUBLAS_STATUS_SUCCESS || found == 0)
     return fail("vf_linear_residual: no cuBLASLt algorithm for rows=%lld k=%d n=%d (status %d)", rows, k, n, (int)s);
   P.algo = res.algo;
@@ -108,7 +154,8 @@ static int linear_residual_impl(const void* x, const void* w, const void* bias, 
   LtPlan plan;
   {
     std::lock_guard<std::mutex> lock(g_lt_mutex);
-    if (!g_lt) VF_LT_TRY(cublasLtCreate(&g_lt));
+    if (int rc = load_lt_api()) return rc;
+    if (!g_lt) VF_LT_TRY(g_api.Create(&g_lt));
     const auto key = std::make_tuple(rows, k, n, ld_x, ld_res, ld_out, dtype * 2 + (bias ? 1 : 0), (int)(workspace_bytes >> 20), batch);
     auto it = g_plans.find(key);
     if (it == g_plans.end()) {
@@ -119,19 +166,19 @@ static int linear_residual_impl(const void* x, const void* w, const void* bias, 
     plan = it->second;
     // the bias pointer is per call (the descriptor is shared by all layers of one shape): set it under the lock and
     // enqueue under the lock as well -- cublasLtMatmul reads the descriptor at enqueue time
-    if (bias) VF_LT_TRY(cublasLtMatmulDescSetAttribute(plan.op, CUBLASLT_MATMUL_DESC_BIAS_POINTER, &bias, sizeof(bias)));
+    if (bias) VF_LT_TRY(g_api.MatmulDescSetAttribute(plan.op, CUBLASLT_MATMUL_DESC_BIAS_POINTER, &bias, sizeof(bias)));
     const float alpha = 1.0f, beta = 1.0f;
     cublasLtMatrixLayout_t d = plan.c;
     cublasLtMatrixLayout_t d_own = nullptr;
     if (ld_out != ld_res) {
       const cudaDataType_t dt = dtype == VF_BF16 ? CUDA_R_16BF : CUDA_R_32F;
-      VF_LT_TRY(cublasLtMatrixLayoutCreate(&d_own, dt, (uint64_t)n, (uint64_t)rows, (int64_t)ld_out));
+      VF_LT_TRY(g_api.MatrixLayoutCreate(&d_own, dt, (uint64_t)n, (uint64_t)rows, (int64_t)ld_out));
       if (batch > 1) if (int rc = set_batch(d_own, batch, rows * ld_out)) return rc;
       d = d_own;
     }
-    cublasStatus_t s = cublasLtMatmul(g_lt, plan.op, &alpha, w, plan.a, x, plan.b, &beta, residual, plan.c, out, d, &plan.algo,
+    cublasStatus_t s = g_api.Matmul(g_lt, plan.op, &alpha, w, plan.a, x, plan.b, &beta, residual, plan.c, out, d, &plan.algo,
                                       workspace, (size_t)workspace_bytes, static_cast<cudaStream_t>(stream));
-    if (d_own) cublasLtMatrixLayoutDestroy(d_own);
+    if (d_own) g_api.MatrixLayoutDestroy(d_own);
     if (s != CUBLAS_STATUS_SUCCESS) return lt_fail(s, "cublasLtMatmul");
   }
   return 0;
