@@ -247,3 +247,16 @@ def test_return_flow_batches_pairs_in_reference_order():
     assert torch.allclose(flow[:, 0, 0, 0], want)
     assert tuple(tf.return_flow(video, estimator, feature_size=8).shape) == (4, 2, 8, 8)
     assert tf.return_flow(video[:1], estimator).shape[0] == 0
+
+
+def test_library_has_no_link_time_cublas_dependency():
+    """libvface_b200.so must bind cuBLASLt at run time (dlopen): a DT_NEEDED entry lets the system libcublasLt shadow
+    PyTorch's copy when the library is loaded before torch, after which torch's own cublasGemmEx fails."""
+    import subprocess
+    from vface_b200 import _lib
+    if not os.path.exists(_lib.LIB_PATH):
+        pytest.skip("library not built")
+    out = subprocess.run(["readelf", "-d", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    needed = [ln for ln in out.splitlines() if "NEEDED" in ln]
+    assert needed, out
+    assert not any("cublas" in ln.lower() for ln in needed), needed
