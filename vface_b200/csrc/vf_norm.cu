@@ -59,7 +59,14 @@ template <> struct V16<__nv_bfloat16> {
 // IEEE division sequence.
 template <typename T> __device__ __forceinline__ float silu_f(float t);
 template <> __device__ __forceinline__ float silu_f<float>(float t) { return t / (1.0f + __expf(-t)); }
-template <> __device__ __forceinline__ float silu_f<__nv_bfloat16>(float t) { return __fdividef(t, 1.0f + __expf(-t)); }
+template <> __device__ __forceinline__ float silu_f<__nv_bfloat16>(float t) {
+  // t sigmoid(t) = h + h tanh(h), h = t / 2: ONE MUFU (tanh.approx, |rel err| < 2^-10.9) instead of EX2 + RCP -- the
+  // apply pass issued 16 MUFU per 16-byte chunk and showed mio_throttle stalls; the result is rounded to bf16.
+  const float h = 0.5f * t;
+  float th;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(h));
+  return fmaf(h, th, h);
+}
 
 // ================================================================================================
 // GroupNorm (NHWC)
@@ -689,6 +696,75 @@ layer_norm_kernel(const LnParams P) {
   }
 }
 
+// Pure LayerNorm for c = 40 L chunks (L = 8, 16, 32: the UNet's 320 / 640 / 1280 channels in bf16): L lanes per
+// row, five 16-byte chunks per lane, 32 / L rows side by side in a warp and kPasses such groups in flight.  The
+// one-row-per-warp mapping above issues two chunk iterations per row at c = 320 with 24 of 32 lanes idle in the
+// second and ten shuffles per row; ncu showed it ISSUE-bound (83 % issue-active at 47 % of DRAM).  Here every lane
+// works in every iteration and a 3-step (L = 8) shuffle serves four rows at once.
+template <typename T, int L, int kPasses>
+__global__ void __launch_bounds__(kLnWarps * 32, 3)
+layer_norm_rows_kernel(const LnParams P) {
+  constexpr int E = V16<T>::E;
+  constexpr int CH = 5;
+  constexpr int kRowsPerPass = 32 / L;
+  const int lane = threadIdx.x & 31;
+  const int sub = lane / L, l = lane % L;                     // row slot within a pass, lane within the row
+  const long long row0 = ((long long)blockIdx.x * kLnWarps + (threadIdx.x >> 5)) * (kRowsPerPass * kPasses);
+  if (row0 >= P.rows) return;
+  uint4 raw[kPasses][CH];
+#pragma unroll
+  for (int p = 0; p < kPasses; ++p) {
+    long long row = row0 + p * kRowsPerPass + sub;
+    if (row >= P.rows) row = P.rows - 1;                       // clamp: recomputed, not stored
+    const T* x = reinterpret_cast<const T*>(P.x) + row * P.c;
+#pragma unroll
+    for (int k = 0; k < CH; ++k) raw[p][k] = ld_nc_v4(x + (l + L * k) * E);
+  }
+  const T* gamma = reinterpret_cast<const T*>(P.gamma);
+  const T* beta = reinterpret_cast<const T*>(P.beta);
+  const float inv_c = 1.0f / (float)P.c;
+#pragma unroll
+  for (int p = 0; p < kPasses; ++p) {
+    const long long row = row0 + p * kRowsPerPass + sub;
+    float sum = 0.f;
+#pragma unroll
+    for (int k = 0; k < CH; ++k) {
+      float v[E];
+      V16<T>::unpack(raw[p][k], v);
+#pragma unroll
+      for (int j = 0; j < E; ++j) sum += v[j];
+    }
+#pragma unroll
+    for (int o = L / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float mean = sum * inv_c;
+    float q = 0.f;
+#pragma unroll
+    for (int k = 0; k < CH; ++k) {
+      float v[E];
+      V16<T>::unpack(raw[p][k], v);
+#pragma unroll
+      for (int j = 0; j < E; ++j) { const float t = v[j] - mean; q = fmaf(t, t, q); }
+    }
+#pragma unroll
+    for (int o = L / 2; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    const float rstd = rsqrtf(q * inv_c + P.eps);
+    const float nmr = -mean * rstd;
+    if (row < P.rows) {
+      T* out = reinterpret_cast<T*>(P.out) + row * P.c;
+#pragma unroll
+      for (int k = 0; k < CH; ++k) {
+        float v[E], g[E], b[E];
+        V16<T>::unpack(raw[p][k], v);
+        V16<T>::ld(gamma + (l + L * k) * E, g);              // 640 B .. 2.5 KB per CTA: L1 hits after the first pass
+        V16<T>::ld(beta + (l + L * k) * E, b);
+#pragma unroll
+        for (int j = 0; j < E; ++j) v[j] = fmaf(fmaf(v[j], rstd, nmr), g[j], b[j]);     // ((v - mean) rstd) g + b
+        st_na_v4(out + (l + L * k) * E, V16<T>::pack(v));
+      }
+    }
+  }
+}
+
 // ================================================================================================
 // GEGLU and residual add
 // ================================================================================================
@@ -939,6 +1015,24 @@ extern "C" int vf_add_layer_norm(const void* x, const void* y, const void* bias,
   if (blocks > 2147483647LL) return fail("vf_add_layer_norm: too many rows");
   cudaStream_t st = (cudaStream_t)stream;
   const int thr = kLnWarps * 32;
+  // the UNet's widths (40 L chunks of 16 bytes, L = 8 / 16 / 32): L lanes per row, several rows per warp
+  const int chunks_total = c / e;
+  const int lanes_per_row = (pure && chunks_total % 5 == 0) ? chunks_total / 5 : 0;
+  if (lanes_per_row == 8 || lanes_per_row == 16 || lanes_per_row == 32) {
+    const int passes = lanes_per_row == 32 ? 2 : lanes_per_row == 16 ? 2 : 2;
+    const long long rows_per_warp = (32 / lanes_per_row) * passes;
+    const long long nb = (rows + kLnWarps * rows_per_warp - 1) / (kLnWarps * rows_per_warp);
+    if (nb > 2147483647LL) return fail("vf_add_layer_norm: too many rows");
+#define VF_LNR_LAUNCH(T)                                                                              \
+    do {                                                                                               \
+      if (lanes_per_row == 8) layer_norm_rows_kernel<T, 8, 2><<<(int)nb, thr, 0, st>>>(P);              \
+      else if (lanes_per_row == 16) layer_norm_rows_kernel<T, 16, 2><<<(int)nb, thr, 0, st>>>(P);       \
+      else layer_norm_rows_kernel<T, 32, 2><<<(int)nb, thr, 0, st>>>(P);                                \
+    } while (0)
+    if (dtype == VF_F32) VF_LNR_LAUNCH(float); else VF_LNR_LAUNCH(__nv_bfloat16);
+#undef VF_LNR_LAUNCH
+    return check_cuda(cudaGetLastError(), "layer_norm_rows_kernel launch");
+  }
 #define VF_LN_LAUNCH(T)                                                                      \
   do {                                                                                       \
     if (pure && per_lane <= 2) layer_norm_kernel<T, 2, 4><<<(int)blocks, thr, 0, st>>>(P);    \
