@@ -72,6 +72,9 @@ template <> __device__ __forceinline__ float silu_f<__nv_bfloat16>(float t) {
 // GroupNorm (NHWC)
 // ================================================================================================
 constexpr int kGnThreads = 256;
+#ifndef VF_GN_MINB
+#define VF_GN_MINB 1
+#endif
 constexpr int kGnMaxGroups = 32;
 
 struct GnParams {
@@ -99,7 +102,7 @@ struct GnMap {
 };
 
 template <typename T, int CPT>    // CPT: chunks per thread along the channel axis (c/E <= 256*CPT)
-__global__ void __launch_bounds__(kGnThreads)
+__global__ void __launch_bounds__(kGnThreads, VF_GN_MINB)
 gn_stats_kernel(const GnParams P) {
   constexpr int E = V16<T>::E;
   // per-(row lane, channel) partials, reduced to groups in a fixed order: bit-reproducible statistics
@@ -188,7 +191,7 @@ gn_stats_kernel(const GnParams P) {
 }
 
 template <typename T, int CPT>
-__global__ void __launch_bounds__(kGnThreads)
+__global__ void __launch_bounds__(kGnThreads, VF_GN_MINB)
 gn_apply_kernel(const GnParams P) {
   constexpr int E = V16<T>::E;
   __shared__ float s_mean[kGnMaxGroups], s_rstd[kGnMaxGroups];
