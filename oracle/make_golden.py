@@ -243,11 +243,32 @@ def golden_vae_decoder():
     save("vae_decoder.npz", z=z.numpy(), out=y.numpy(), keys=np.array(sorted(sd.keys())))
 
 
+def golden_vae_encoder():
+    """Reference first-stage Encoder (model.py:368-459) + quant_conv (autoencoder.py:304, :322-326) on the reduced
+    ddconfig, weights from vface_b200.synth (seed 5): image -> posterior moments; plus the posterior's mean / std."""
+    from ldm.modules.diffusionmodules.model import Encoder
+    from ldm.modules.distributions.distributions import DiagonalGaussianDistribution
+    from vface_b200 import synth
+    with quiet():
+        enc = Encoder(**VAE_SMALL).eval()
+    qc = torch.nn.Conv2d(8, 8, 1)
+    sd = synth.synth_state_dict({**{"encoder." + k: v for k, v in enc.state_dict().items()},
+                                 **{"quant_conv." + k: v for k, v in qc.state_dict().items()}}, seed=5)
+    enc.load_state_dict({k[len("encoder."):]: v for k, v in sd.items() if k.startswith("encoder.")})
+    qc.load_state_dict({k[len("quant_conv."):]: v for k, v in sd.items() if k.startswith("quant_conv.")})
+    x = torch.randn(2, 3, 64, 64, generator=torch.Generator().manual_seed(22))
+    with torch.no_grad():
+        moments = qc(enc(x))
+        post = DiagonalGaussianDistribution(moments)
+    save("vae_encoder.npz", x=x.numpy(), moments=moments.numpy(), mean=post.mean.numpy(), std=post.std.numpy(),
+         keys=np.array(sorted(sd.keys())))
+
+
 def main():
     if not rh.available():
         sys.exit("reference not mounted; golden vectors can only be generated in the build container")
     rh.install()
-    which = sys.argv[1:] or ["fsai", "warp", "attn_hooks", "schedule", "sampler_small", "unet_full", "sampler_full", "vae_decoder"]
+    which = sys.argv[1:] or ["fsai", "warp", "attn_hooks", "schedule", "sampler_small", "unet_full", "sampler_full", "vae_decoder", "vae_encoder"]
     for w in which:
         globals()["golden_" + w]()
 

@@ -84,3 +84,57 @@ def test_decoded_frames_psnr_bf16_sampler_vs_reference(kind):
     assert 0.02 < img.std().item() and 0.05 < img.mean().item() < 0.95
     p = psnr(a, b)
     assert p >= 40.0, p
+
+
+# ---- encoder half (the save loop's encode -> decode round trip, scripts/VFace_inference_batch.py:456-459, :603-623) ----
+def _autoencoder(dtype, seed_dec=3, seed_enc=5):
+    from vface_b200 import synth
+    from vface_b200.ldm.modules.diffusionmodules.model import AutoencoderKL
+    m = AutoencoderKL(VAE_SMALL)
+    sd = m.state_dict()
+    dec = synth.synth_state_dict({k: v for k, v in sd.items() if k.startswith(("decoder.", "post_quant_conv."))}, seed=seed_dec)
+    enc = synth.synth_state_dict({k: v for k, v in sd.items() if k.startswith(("encoder.", "quant_conv."))}, seed=seed_enc)
+    m.load_state_dict({**dec, **enc})
+    return m.cuda().eval().to(dtype)
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-4), (torch.bfloat16, 3e-2)])
+def test_encoder_vs_reference_golden(dtype, tol):
+    """Encoder + quant_conv against the UNMODIFIED reference (tests/golden/vae_encoder.npz), same state-dict keys."""
+    gold = np.load(os.path.join(GOLD, "vae_encoder.npz"))
+    m = _autoencoder(dtype)
+    enc_keys = sorted(k for k in m.state_dict() if k.startswith(("encoder.", "quant_conv.")))
+    assert enc_keys == list(gold["keys"])
+    x = torch.from_numpy(gold["x"]).cuda()
+    with torch.no_grad():
+        post = m.encode(x.to(dtype))
+    want = torch.from_numpy(gold["moments"]).cuda()
+    assert tuple(post.parameters.shape) == tuple(want.shape)
+    err = ((post.parameters.float() - want).norm() / want.norm()).item()
+    assert err < tol, err
+    assert ((post.mean.float() - torch.from_numpy(gold["mean"]).cuda()).norm() / want.norm()).item() < tol
+    if dtype == torch.float32:
+        assert torch.allclose(post.std, torch.from_numpy(gold["std"]).cuda(), rtol=2e-3, atol=1e-6)
+        assert torch.equal(post.mode(), post.mean)
+        g = torch.Generator().manual_seed(1)
+        z = post.sample(generator=g)
+        assert z.shape == post.mean.shape and torch.isfinite(z).all()
+
+
+def test_encode_decode_surface():
+    """LatentDiffusion.encode_first_stage / get_first_stage_encoding / decode_first_stage keep the reference's contract
+    (ddpm.py:782-791, :1277-1330): z = scale_factor * posterior sample, x' = decoder(post_quant_conv(z / scale_factor))."""
+    from vface_b200.latent_diffusion import LatentDiffusion
+    model = LatentDiffusion(unet_config=dict(model_channels=32, num_heads=2), first_stage_config=VAE_SMALL, first_stage_encoder=True)
+    model.first_stage_model.load_state_dict(_autoencoder(torch.float32).state_dict())
+    model = model.cuda().eval()
+    gold = np.load(os.path.join(GOLD, "vae_encoder.npz"))
+    x = torch.from_numpy(gold["x"]).cuda()
+    with torch.no_grad():
+        post = model.encode_first_stage(x)
+        z = model.get_first_stage_encoding(post.mode())
+        assert torch.allclose(z, 0.18215 * torch.from_numpy(gold["mean"]).cuda(), rtol=1e-3, atol=1e-5)
+        y = model.decode_first_stage(z)
+    assert tuple(y.shape) == (2, 3, 64, 64) and torch.isfinite(y).all()
+    with pytest.raises(RuntimeError):
+        LatentDiffusion(unet_config=dict(model_channels=32, num_heads=2), first_stage_config=VAE_SMALL).encode_first_stage(x)

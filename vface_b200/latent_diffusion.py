@@ -38,7 +38,7 @@ class DiffusionWrapper(nn.Module):
 
 class LatentDiffusion(nn.Module):
     def __init__(self, unet_config=None, timesteps=1000, linear_start=0.00085, linear_end=0.012, unet=None,
-                 first_stage_config=None):
+                 first_stage_config=None, first_stage_encoder=False):
         super().__init__()
         cfg = dict(REFACE_UNET_CONFIG)
         if unet_config:
@@ -49,8 +49,9 @@ class LatentDiffusion(nn.Module):
         self.scale_factor = 0.18215
         # the step after the path: only built on request, `{}` = the REFace ddconfig
         if first_stage_config is not None:
-            from .ldm.modules.diffusionmodules.model import AutoencoderKLDecoder
-            self.first_stage_model = AutoencoderKLDecoder(first_stage_config or None)
+            from .ldm.modules.diffusionmodules.model import AutoencoderKL, AutoencoderKLDecoder
+            cls = AutoencoderKL if first_stage_encoder else AutoencoderKLDecoder
+            self.first_stage_model = cls(first_stage_config or None)
         betas = make_beta_schedule("linear", timesteps, linear_start=linear_start, linear_end=linear_end)
         alphas_cumprod = np.cumprod(1.0 - betas, axis=0)
         alphas_cumprod_prev = np.append(1.0, alphas_cumprod[:-1])
@@ -82,6 +83,19 @@ class LatentDiffusion(nn.Module):
             raise RuntimeError("LatentDiffusion was built without first_stage_config")
         p = next(self.first_stage_model.parameters())
         return self.first_stage_model.decode((1.0 / self.scale_factor * z).to(p.dtype))
+
+    def encode_first_stage(self, x):
+        """ddpm.py:1307-1330 (plain path) -> AutoencoderKL.encode: the posterior over the latents of image x."""
+        fs = getattr(self, "first_stage_model", None)
+        if fs is None or not hasattr(fs, "encode"):
+            raise RuntimeError("LatentDiffusion was built without first_stage_encoder=True")
+        p = next(fs.parameters())
+        return fs.encode(x.to(p.dtype))
+
+    def get_first_stage_encoding(self, encoder_posterior):
+        """ddpm.py:782-791: scale_factor * (a sample of the posterior, or the tensor itself)."""
+        z = encoder_posterior.sample() if hasattr(encoder_posterior, "sample") else encoder_posterior
+        return self.scale_factor * z
 
     def to_compute_dtype(self, dtype):
         """Cast the UNet parameters (bf16 on the throughput path); schedule buffers stay fp32."""

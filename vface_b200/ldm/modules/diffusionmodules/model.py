@@ -12,7 +12,9 @@ Execution plan: channels-last activations in the parameter dtype, GroupNorm+SiLU
 The single mid-block attention is one head of width C = 512 over N = h*w tokens: wider than the fused
 tcgen05 kernel's TMEM budget (d_head <= 192), so it goes through vf_attn_fwd only when C <= 192 (reduced
 test configurations) and through torch's scaled_dot_product_attention (a library call, off the hot path)
-otherwise.  Encoder and the training losses are out of scope.
+otherwise.  The Encoder (:368-459) + quant_conv + DiagonalGaussianDistribution (distributions.py:24-45) are
+mirrored the same way for the encode -> decode round trip of the script's save loop
+(scripts/VFace_inference_batch.py:456-459, :603-623); the training losses are out of scope.
 """
 from __future__ import annotations
 
@@ -46,6 +48,22 @@ class Upsample(nn.Module):
     def forward(self, x):
         x = ops.upsample_nearest2x(x)                    # F.interpolate(scale_factor=2.0, mode="nearest"), channels-last
         return self.conv(x) if self.with_conv else x
+
+
+class Downsample(nn.Module):
+    """Stride-2 3x3 convolution over the input padded by one zero row/column at the bottom/right (reference :60-79:
+    `pad = (0, 1, 0, 1)`, "no asymmetric padding in torch conv")."""
+
+    def __init__(self, in_channels, with_conv):
+        super().__init__()
+        self.with_conv = with_conv
+        if with_conv:
+            self.conv = nn.Conv2d(in_channels, in_channels, kernel_size=3, stride=2, padding=0)
+
+    def forward(self, x):
+        if not self.with_conv:
+            return F.avg_pool2d(x, kernel_size=2, stride=2)
+        return self.conv(F.pad(x, (0, 1, 0, 1), mode="constant", value=0))
 
 
 class ResnetBlock(nn.Module):
@@ -175,6 +193,92 @@ class Decoder(nn.Module):
         return torch.tanh(h) if self.tanh_out else h
 
 
+class Encoder(nn.Module):
+    """Reference :368-459, same module tree (conv_in, down.{level}.block.{i}, down.{level}.downsample.conv,
+    mid.block_1 / attn_1 / block_2, norm_out, conv_out): image (n, in_channels, H, W) -> moments (n, 2 z, H/8, W/8)."""
+
+    def __init__(self, *, ch, out_ch, ch_mult=(1, 2, 4, 8), num_res_blocks, attn_resolutions, dropout=0.0,
+                 resamp_with_conv=True, in_channels, resolution, z_channels, double_z=True, use_linear_attn=False,
+                 attn_type="vanilla", **ignore_kwargs):
+        super().__init__()
+        if use_linear_attn or attn_type != "vanilla":
+            raise NotImplementedError("only vanilla attention is used by the REFace first stage")
+        self.ch, self.temb_ch = ch, 0
+        self.num_resolutions = len(ch_mult)
+        self.num_res_blocks = num_res_blocks
+        self.resolution, self.in_channels = resolution, in_channels
+        self.conv_in = nn.Conv2d(in_channels, ch, kernel_size=3, stride=1, padding=1)
+        curr_res = resolution
+        in_ch_mult = (1,) + tuple(ch_mult)
+        self.down = nn.ModuleList()
+        block_in = ch
+        for i_level in range(self.num_resolutions):
+            block, attn = nn.ModuleList(), nn.ModuleList()
+            block_in = ch * in_ch_mult[i_level]
+            block_out = ch * ch_mult[i_level]
+            for _ in range(num_res_blocks):
+                block.append(ResnetBlock(in_channels=block_in, out_channels=block_out, temb_channels=0, dropout=dropout))
+                block_in = block_out
+                if curr_res in attn_resolutions:
+                    attn.append(AttnBlock(block_in))
+            down = nn.Module()
+            down.block, down.attn = block, attn
+            if i_level != self.num_resolutions - 1:
+                down.downsample = Downsample(block_in, resamp_with_conv)
+                curr_res //= 2
+            self.down.append(down)
+        self.mid = nn.Module()
+        self.mid.block_1 = ResnetBlock(in_channels=block_in, out_channels=block_in, temb_channels=0, dropout=dropout)
+        self.mid.attn_1 = AttnBlock(block_in)
+        self.mid.block_2 = ResnetBlock(in_channels=block_in, out_channels=block_in, temb_channels=0, dropout=dropout)
+        self.norm_out = Normalize(block_in)
+        self.conv_out = nn.Conv2d(block_in, 2 * z_channels if double_z else z_channels, kernel_size=3, stride=1, padding=1)
+
+    def forward(self, x):
+        if x.dtype == torch.float32:
+            with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+                return self._forward(x)
+        return self._forward(x)
+
+    def _forward(self, x):
+        if not getattr(self, "_weights_channels_last", False):
+            self.to(memory_format=torch.channels_last)
+            self._weights_channels_last = True
+        h = self.conv_in(x.contiguous(memory_format=torch.channels_last))
+        for i_level in range(self.num_resolutions):
+            for i_block in range(self.num_res_blocks):
+                h = self.down[i_level].block[i_block](h)
+                if len(self.down[i_level].attn) > 0:
+                    h = self.down[i_level].attn[i_block](h)
+            if i_level != self.num_resolutions - 1:
+                h = self.down[i_level].downsample(h)
+        h = self.mid.block_1(h)
+        h = self.mid.attn_1(h)
+        h = self.mid.block_2(h)
+        return F.conv2d(_gn_silu(self.norm_out, _nhwc(h)).permute(0, 3, 1, 2), self.conv_out.weight, self.conv_out.bias, padding=1)
+
+
+class DiagonalGaussianDistribution:
+    """distributions.py:24-45: moments (n, 2 z, h, w) -> mean, logvar clamped to [-30, 20], std, var; sample / mode."""
+
+    def __init__(self, parameters, deterministic=False):
+        self.parameters = parameters
+        self.mean, self.logvar = torch.chunk(parameters, 2, dim=1)
+        self.logvar = torch.clamp(self.logvar, -30.0, 20.0)
+        self.deterministic = deterministic
+        self.std = torch.exp(0.5 * self.logvar)
+        self.var = torch.exp(self.logvar)
+        if deterministic:
+            self.var = self.std = torch.zeros_like(self.mean)
+
+    def sample(self, generator=None):
+        noise = torch.randn(self.mean.shape, generator=generator).to(device=self.parameters.device, dtype=self.mean.dtype)
+        return self.mean + self.std * noise
+
+    def mode(self):
+        return self.mean
+
+
 # configs/project_ffhq.yaml first_stage_config.params.ddconfig
 REFACE_DDCONFIG = dict(double_z=True, z_channels=4, resolution=256, in_channels=3, out_ch=3, ch=128,
                        ch_mult=[1, 2, 4, 4], num_res_blocks=2, attn_resolutions=[], dropout=0.0)
@@ -196,3 +300,24 @@ class AutoencoderKLDecoder(nn.Module):
             with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
                 return self.decoder(self.post_quant_conv(z))
         return self.decoder(self.post_quant_conv(z))
+
+
+class AutoencoderKL(AutoencoderKLDecoder):
+    """Both halves of AutoencoderKL (autoencoder.py:285-333): encoder + quant_conv in front of the decode half, same
+    state-dict keys as the reference's `first_stage_model.*` (minus the training loss)."""
+
+    def __init__(self, ddconfig=None, embed_dim=4):
+        super().__init__(ddconfig, embed_dim)
+        cfg = dict(REFACE_DDCONFIG)
+        if ddconfig:
+            cfg.update(ddconfig)
+        if not cfg.get("double_z", True):
+            raise ValueError("AutoencoderKL needs double_z (autoencoder.py:303)")
+        self.encoder = Encoder(**cfg)
+        self.quant_conv = nn.Conv2d(2 * cfg["z_channels"], 2 * embed_dim, 1)
+
+    def encode(self, x):
+        if x.dtype == torch.float32:
+            with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+                return DiagonalGaussianDistribution(self.quant_conv(self.encoder(x)))
+        return DiagonalGaussianDistribution(self.quant_conv(self.encoder(x)))
