@@ -35,7 +35,7 @@ namespace vf {
 
 using namespace sm100;
 
-constexpr int kGemmThreads = 256;
+constexpr int kGemmThreads = 384;     // warp 0 TMA, 1 MMA, 2-3 idle, 4-7 epilogue, 8-11 second epilogue group (streaming kernel only)
 constexpr int kGemmBM = 128;          // rows per tile
 constexpr int kGemmBN = 128;          // OUTPUT columns per tile (256 accumulator columns: value + gate)
 constexpr int kGemmBK = 64;           // k-block: 64 bf16 = one 128-byte swizzled row
@@ -155,7 +155,7 @@ gemm_geglu_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     mbar_init(&bars.w_full, 1);
     for (int a = 0; a < 2; ++a) {
       mbar_init(&bars.acc_full[a], 1);
-      mbar_init(&bars.acc_empty[a], 4);            // one arrival per epilogue warp
+      mbar_init(&bars.acc_empty[a], kWResident ? 4 : 8);            // one arrival per epilogue warp
     }
     fence_barrier_init();
   }
@@ -232,11 +232,17 @@ gemm_geglu_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         tc_commit(&bars.acc_full[ab]);
       }
     }
-  } else if (warp >= 4) {
+  } else if (warp >= 4 && (!kWResident || warp < 8)) {
     // =========================== epilogue ========================================================
+    // Eight epilogue warps: warps 4-7 and 8-11 both cover the four TMEM lane quarters (a warp may touch quarter
+    // warp % 4) and split the column steps of every tile.  With four, ONE warp per scheduler had to push the ~12
+    // issue slots per output element at single-warp IPC.  Measured: k = 640 0.567 -> 0.539 ms, k = 1280 0.480 -> 0.465;
+    // the W-resident kernel (k = 320) got SLOWER with eight (0.659 -> 0.739 ms) and keeps four.
+    constexpr int kEpiGroups = kWResident ? 1 : 2;
     const int quarter = warp & 3;
+    const int ehalf = (warp - 4) >> 2;                       // group 0: the first half of the column steps, 1: the rest
     const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
-    const int et = threadIdx.x - 128;                        // 0..127
+    const int et = threadIdx.x - 128;                        // 0..255; the first 128 stage the bias
     uint32_t ti = 0;
     for (TileWalk<kWResident> tw(P); tw.valid(); tw.next(), ++ti) {
       const int mb = tw.mb(), nb = tw.nb();
@@ -246,9 +252,11 @@ gemm_geglu_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       // (W-resident: the n-block never changes, one set filled on the first tile)
       const uint32_t bs = kWResident ? 0u : ab;
       if (!kWResident || ti == 0) {
-        s_bias[bs][et] = P.bias ? __bfloat162float(P.bias[nb * kGemmBN + et]) : 0.0f;
-        s_bias[bs][kGemmBN + et] = P.bias ? __bfloat162float(P.bias[P.n + nb * kGemmBN + et]) : 0.0f;
-        named_bar_sync(1, 128);
+        if (et < kGemmBN) {
+          s_bias[bs][et] = P.bias ? __bfloat162float(P.bias[nb * kGemmBN + et]) : 0.0f;
+          s_bias[bs][kGemmBN + et] = P.bias ? __bfloat162float(P.bias[P.n + nb * kGemmBN + et]) : 0.0f;
+        }
+        named_bar_sync(1, 128 * kEpiGroups);
       }
       mbar_wait(&bars.acc_full[ab], ause & 1);
       tc_fence_after();
@@ -256,7 +264,7 @@ gemm_geglu_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       const long long row = (long long)mb * kGemmBM + quarter * 32 + lane;
       __nv_bfloat16* orow = P.out + row * P.n + (long long)nb * kGemmBN;
 #pragma unroll 1
-      for (int c = 0; c < kGemmBN / 32; ++c) {
+      for (int c = ehalf * (kGemmBN / 32 / kEpiGroups); c < (ehalf + 1) * (kGemmBN / 32 / kEpiGroups); ++c) {
         uint32_t v[32], g[32];
         tmem_ld_x32(acc + c * 32, v);
         tmem_ld_x32(acc + kGemmBN + c * 32, g);
@@ -361,7 +369,7 @@ extern "C" int vf_linear_geglu(const void* x, const void* w, const void* bias, v
       attr_r = smem_res;
     }
     const int groups = num_sms() / P.n_blocks;
-    gemm_geglu_kernel<true><<<groups * P.n_blocks, kGemmThreads, smem_res, (cudaStream_t)stream>>>(ma, mw, P);
+    gemm_geglu_kernel<true><<<groups * P.n_blocks, 256, smem_res, (cudaStream_t)stream>>>(ma, mw, P);
     return check_cuda(cudaGetLastError(), "gemm_geglu_kernel<resident W> launch");
   }
   const size_t smem = 1008 + (size_t)kGemmStages * kStageBytes + kTail;
