@@ -207,6 +207,31 @@ def golden_sampler_full():
          pred_x0=torch.stack(inter["pred_x0"][1:]).numpy())
 
 
+def golden_sampler_full_s10():
+    """BASELINE.json configs[0] at reduced frame count: the FULL-SIZE UNet through the reference sampler, DDIM 10 steps,
+    2 frames, CFG 3.0, hooks on (integer-valued flow: the floor indices of the warp sit exactly on pixel centres).
+    ~5 minutes on 8 cores; only the per-step latents are kept (fp16-rounded differences would defeat the purpose, so
+    they stay fp32: 1.3 MB)."""
+    from vface_b200 import synth
+    from . import kernels as ok
+    ref = rh.build_reference_unet()
+    ref.load_state_dict(synth.synth_state_dict(ref.state_dict(), seed=1))
+    B, S = 2, 10
+    steps = ok.make_schedule(S)["ddim_timesteps"]
+    clip = synth.synth_clip(B, steps=steps, flow_kind="integer")
+    sampler = rh.build_reference_sampler(ref)
+    d = tempfile.mkdtemp()
+    for t, v in clip["inversion"].items():
+        torch.save(v, os.path.join(d, f"ddim_latents_{t}.pt"))
+    with quiet():
+        samples, inter = sampler.sample(
+            S=S, batch_size=B, shape=(4, 64, 64), conditioning=clip["c"], target_conditioning=clip["target_cond"],
+            inverse_results_dir=d, x_T=clip["x_T"], flow=clip["flow"], unconditional_guidance_scale=3.0,
+            unconditional_conditioning=clip["uc"], eta=0.0, verbose=False, log_every_t=1,
+            test_model_kwargs=dict(inpaint_image=clip["inpaint_image"], inpaint_mask=clip["inpaint_mask"]))
+    save("sampler_full_s10.npz", x_inter=torch.stack(inter["x_inter"][1:]).numpy())
+
+
 def golden_unet_full():
     """One forward of the full-size UNet (project_ffhq.yaml) on a 3-way batch of one frame."""
     from vface_b200 import synth
@@ -268,7 +293,7 @@ def main():
     if not rh.available():
         sys.exit("reference not mounted; golden vectors can only be generated in the build container")
     rh.install()
-    which = sys.argv[1:] or ["fsai", "warp", "attn_hooks", "schedule", "sampler_small", "unet_full", "sampler_full", "vae_decoder", "vae_encoder"]
+    which = sys.argv[1:] or ["fsai", "warp", "attn_hooks", "schedule", "sampler_small", "unet_full", "sampler_full", "sampler_full_s10", "vae_decoder", "vae_encoder"]
     for w in which:
         globals()["golden_" + w]()
 

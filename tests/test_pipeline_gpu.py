@@ -93,6 +93,23 @@ def test_sampler_full_size_vs_reference_golden(dtype, tol):
     assert rel_l2(samples, gold["samples"]) < tol
 
 
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-4), (torch.bfloat16, 1e-2)])
+def test_sampler_full_size_ddim10_vs_reference_golden(dtype, tol):
+    """BASELINE.json configs[0] (DDIM 10 steps, CFG 3.0, hooks on) on the full-size UNet, 2 frames, integer-valued flow:
+    all ten per-step latents against the unmodified reference run on CPU (tests/golden/sampler_full_s10.npz)."""
+    from oracle import kernels as ok
+    from vface_b200 import synth
+    gold = np.load(os.path.join(GOLD, "sampler_full_s10.npz"))
+    _, sampler, _ = build(None, dtype)
+    S, B = 10, 2
+    clip = synth.synth_clip(B, steps=ok.make_schedule(S)["ddim_timesteps"], flow_kind="integer")
+    _, inter = run_sample(sampler, clip, S, B, clip["inversion"])
+    want = gold["x_inter"]
+    assert want.shape[0] == S
+    errs = [rel_l2(inter["x_inter"][1 + i], want[i]) for i in range(S)]
+    assert max(errs) < tol, errs
+
+
 def test_ddim50_full_size_bf16_per_step_error():
     """BASELINE.json's configuration (DDIM-50, CFG 3.0, full-size UNet, hooks on): every per-step latent of the bf16
     path within 1e-2 relative L2 of the fp32 path of the same kernels -- which reproduces the unmodified reference to
