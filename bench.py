@@ -134,13 +134,25 @@ def local_clip(frames, rank, steps):
     return clip
 
 
-def workload_config(frames, world, n_branches=3):
+CPU_ARM_FRAMES = 2      # frames per step the CPU arm (oracle port) actually runs
+
+
+def workload_config(frames, world, n_branches=3, strong=False):
     """The `config` object of the JSON line -- identical for the vface_b200 arm and the reference arm."""
-    return dict(workload="VFace full pipeline, 32-frame 512x512 clip per GPU, DDIM-50 with CFG 3.0, bf16",
+    workload = "VFace full pipeline, 32-frame 512x512 clip per GPU, DDIM-50 with CFG 3.0, bf16"
+    if strong:      # BASELINE.json configs[4]
+        workload = (f"{frames * world}-frame 512x512 clip sharded by frame across {world} B200 with NCCL halo exchange of boundary "
+                    f"attention features, DDIM-50 with CFG 3.0, bf16")
+    return dict(workload=workload,
+                scope="denoising loop only: 50 x (3-branch UNet forward with the VFace hooks + CFG/DDIM update); VAE, DDIM "
+                      "inversion and flow estimation run once per clip outside the loop and are not timed",
                 frames_per_gpu=frames, total_frames=frames * world, ddim_steps=DDIM_STEPS, cfg_scale=CFG_SCALE,
                 unet_batch_per_step=n_branches * frames, branches=n_branches, parallelism=f"frame-shard x{world}",
                 l2="step working set (1.7 GB weights + activations) far exceeds the 126 MB L2; no flush needed",
-                weights="random-init REFace UNet 859.5M params, zero-modules re-randomised (seed 1)")
+                weights="random-init REFace UNet 859.5M params, zero-modules re-randomised (seed 1)",
+                cpu_arm_sample=f"the CPU arm (--impl reference, and cpu_baseline) times a bounded sample of this workload: "
+                               f"{CPU_ARM_FRAMES} of the frames per step (UNet batch {3 * CPU_ARM_FRAMES}, hooks and flow warp on), "
+                               f"one host process, frames/s normalised per frame")
 
 
 # ---- CPU baseline (oracle port) -------------------------------------------------------------------------------
@@ -181,7 +193,7 @@ def run_reference_arm(args, rank):
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     sd = synth.synth_state_dict(LatentDiffusion().model.diffusion_model.state_dict(), seed=1)
-    frames = 2
+    frames = CPU_ARM_FRAMES
     # bounded: two frames per step (so that the flow warp between frames is exercised); at most ~5 minutes in total
     t_probe, _ = cpu_step_seconds(sd, frames, 0, 1)
     budget = 300.0
@@ -209,6 +221,104 @@ def run_reference_arm(args, rank):
     print(json.dumps(line), flush=True)
 
 
+# ---- per-kernel rooflines of the memory-bound kernels (timed live inside steps of the bench loop) ---------------------
+def summarize_secondary(events, n_steps, pk):
+    """{kind: [(ms, work, unit), ...]} from ops.profile_kernels -> one row per kernel kind.  `work` is the ALGORITHMIC bytes
+    (or flops) of the launch as DESIGN.md section 3 defines them; fractions are of the measured peaks."""
+    rows = []
+    for kind, evs in sorted(events.items()):
+        ms = float(np.sum([e[0] for e in evs]))
+        work = float(np.sum([e[1] for e in evs]))
+        unit = evs[0][2]
+        if ms <= 0:
+            continue
+        if unit == "B":
+            ach = work / (ms * 1e-3) / 1e9
+            rows.append(dict(kernel=kind, bound="hbm", launches_per_step=len(evs) / n_steps, ms_per_step=ms / n_steps,
+                             algorithmic_bytes_per_step=work / n_steps, achieved=ach, unit="GB/s", peak=pk["hbm"], frac=ach / pk["hbm"]))
+        else:
+            ach = work / (ms * 1e-3) / 1e12
+            rows.append(dict(kernel=kind, bound="tensor", launches_per_step=len(evs) / n_steps, ms_per_step=ms / n_steps,
+                             algorithmic_flops_per_step=work / n_steps, achieved=ach, unit="TFLOP/s", peak=pk["tc_sustained"],
+                             frac=ach / pk["tc_sustained"]))
+    rows.sort(key=lambda r: -r["ms_per_step"])
+    return dict(peak_source=f"{pk['src']} (MEASURED_PEAKS.json): HBM copy {pk['hbm']} GB/s, bf16 sustained {pk['tc_sustained']} TF/s",
+                how="CUDA event pair around every vface_b200 launch during 2 extra steps of the timed loop (same shapes, same stream)",
+                kernels=rows)
+
+
+# ---- sharded == unsharded (SURVEY.md section 4, D1) ----------------------------------------------------------------------
+def shard_vs_single(sampler, rank, world, device, frames_per_rank, ddim_steps, seed=23):
+    """ONE clip of frames_per_rank * world frames through DDIMSampler.sample twice: sharded by contiguous frame chunk over
+    the ranks (halo over NCCL), and whole on every rank (no shard active).  Returns the comparison (rank 0's view)."""
+    import torch.distributed as dist
+    from vface_b200 import synth
+    total = frames_per_rank * world
+    sampler.make_schedule(ddim_steps, ddim_eta=0.0, verbose=False)
+    clip = synth.synth_clip(total, seed=seed, steps=sampler.ddim_timesteps)
+    g = lambda t: t.to(device)
+
+    def sample(sh):
+        from vface_b200 import frame_shard
+        frame_shard.activate(sh)
+        take = (lambda t: t) if sh is None else sh.take
+        flow = clip["flow"] if sh is None else sh.local_flow(clip["flow"])
+        inv = {t: g(take(v)) for t, v in clip["inversion"].items()}
+        out, _ = sampler.sample(
+            S=ddim_steps, batch_size=total if sh is None else sh.frames, shape=(4, 64, 64), conditioning=g(take(clip["c"])),
+            target_conditioning=g(take(clip["target_cond"])), inverse_results_dir=inv, x_T=g(take(clip["x_T"])),
+            flow=[g(f) for f in flow], unconditional_guidance_scale=CFG_SCALE, unconditional_conditioning=g(take(clip["uc"])),
+            eta=0.0, verbose=False,
+            test_model_kwargs=dict(inpaint_image=g(take(clip["inpaint_image"])), inpaint_mask=g(take(clip["inpaint_mask"]))))
+        return out
+
+    from vface_b200 import frame_shard
+    sh = frame_shard.FrameShard(rank, world, total)
+    with torch.no_grad():
+        part = sample(sh)
+        gathered = sh.gather_frames(part)
+        whole = sample(None)
+    frame_shard.activate(None)
+    sampler.make_schedule(DDIM_STEPS, ddim_eta=0.0, verbose=False)
+    diff = (gathered.double() - whole.double())
+    rel = (diff.norm() / whole.double().norm()).item()
+    # the ranks computed `whole` independently on identical inputs: it must agree bit for bit across GPUs
+    ref = whole.clone()
+    if world > 1:
+        dist.broadcast(ref, 0)
+    same_whole = torch.tensor([float(torch.equal(ref, whole))], device=device)
+    if world > 1:
+        dist.all_reduce(same_whole, op=dist.ReduceOp.MIN)
+    own = slice(sh.lo, sh.hi)
+    return dict(total_frames=total, frames_per_rank=frames_per_rank, ddim_steps=ddim_steps, dtype=str(whole.dtype),
+                model_dtype=str(next(sampler.model.model.diffusion_model.parameters()).dtype),
+                rel_l2_sharded_vs_single=rel, max_abs=diff.abs().max().item(), bit_exact=bool(torch.equal(gathered, whole)),
+                own_frames_bit_exact=bool(torch.equal(part, whole[own])),
+                single_gpu_runs_identical_across_ranks=bool(same_whole.item() == 1.0),
+                halo_messages=sh.halo_messages, shard_bounds=frame_shard.shard_bounds(total, world))
+
+
+def verify_shard(rank, world, device):
+    """--verify-shard: the strict form of D1 in the fp32 reference-precision path (and bf16 beside it): a 2-frames-per-rank
+    clip, 3 DDIM steps with hooks and flow, sharded over the ranks vs whole on one GPU; fp32 must agree to <= 1e-5."""
+    from vface_b200.ldm.models.diffusion.ddim_w_inv import DDIMSampler
+    res = {}
+    ok = True
+    for name, dt in (("fp32", torch.float32), ("bf16", torch.bfloat16)):
+        model, _ = build_model(device, dt)
+        sampler = DDIMSampler(model)
+        r = shard_vs_single(sampler, rank, world, device, frames_per_rank=2, ddim_steps=3)
+        res[name] = r
+        if name == "fp32":
+            ok = ok and r["rel_l2_sharded_vs_single"] <= 1e-5
+        del model, sampler
+        torch.cuda.empty_cache()
+    if rank == 0:
+        print(json.dumps(dict(verify_shard=res, n_gpus=world, passed=bool(ok))), flush=True)
+    if not ok:
+        sys.exit(1)
+
+
 # ---- main arm ---------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
@@ -221,6 +331,13 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--elide-recon", action="store_true", help="skip the output-dead recon branch (SURVEY.md F3)")
     ap.add_argument("--no-elide-extra", action="store_true", help="skip the secondary elided-recon measurement")
+    ap.add_argument("--total-frames", type=int, default=0,
+                    help="strong scaling: ONE clip of this many frames split over the ranks (BASELINE.json configs[4]: 256); "
+                         "overrides --frames")
+    ap.add_argument("--no-clip256", action="store_true", help="skip the secondary 256-frame strong-scaling measurement")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the per-kernel roofline_secondary pass")
+    ap.add_argument("--verify-shard", action="store_true",
+                    help="correctness only (SURVEY.md section 4, D1): one clip sharded over the ranks == the same clip on one rank")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -245,45 +362,90 @@ def main():
         dist.init_process_group("nccl", device_id=device)
     W = max(args.warmup, 3)
     K = max(args.steps, 1)
-    frames = args.frames
+    strong = args.total_frames > 0
+    if strong:
+        if args.total_frames % world:
+            sys.exit(f"--total-frames {args.total_frames} must divide by the {world} ranks")
+        frames = args.total_frames // world
+    else:
+        frames = args.frames
     total_frames = frames * world
+    if args.verify_shard:
+        verify_shard(rank, world, device)
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
     model, sd = build_model(device, torch.bfloat16)
     sampler = DDIMSampler(model, elide_dead_recon=args.elide_recon)
     sampler.make_schedule(DDIM_STEPS, ddim_eta=0.0, verbose=False)
     steps = sampler.ddim_timesteps
-    shard = frame_shard.FrameShard(rank, world, total_frames)
-    frame_shard.activate(shard)
-
-    clip = local_clip(frames, rank, steps)
-    pin = lambda t: t.pin_memory()
-    host = {k: pin(v) for k, v in clip.items() if isinstance(v, torch.Tensor)}
-    host_flow = pin(torch.cat(clip["flow"], dim=0))
-    host_inv = {t: pin(v) for t, v in clip["inversion"].items()}
-    dev = {k: v.to(device) for k, v in host.items()}
-    dev_flow = host_flow.to(device)
-    dev_inv = {t: v.to(device) for t, v in host_inv.items()}
-    kw = dict(test_model_kwargs=dict(inpaint_image=dev["inpaint_image"], inpaint_mask=dev["inpaint_mask"]))
-    sampler._register_hooks(dev_flow)
-    sampler._inv_cache = dev_inv
     time_range = np.flip(steps)
-
-    def one_step(i, x):
-        i = i % DDIM_STEPS
-        step = int(time_range[i])
-        ts = torch.full((frames,), step, device=device, dtype=torch.long)
-        x_prev, _ = sampler.p_sample_ddim_with_inverse(
-            x, dev["c"], ts, index=DDIM_STEPS - 1 - i, target_conditioning=dev["target_cond"],
-            inverse_results_dir=dev_inv, unconditional_guidance_scale=CFG_SCALE,
-            unconditional_conditioning=dev["uc"], flow=dev_flow, _step=step, **kw)
-        return x_prev
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    x = dev["x_T"]
+    class Runner:
+        """One rank's shard (`n` frames) of a clip of n * world frames, resident in HBM, and the step over it."""
+
+        def __init__(self, n, pinned=True):
+            self.n = n
+            self.shard = frame_shard.FrameShard(rank, world, n * world)
+            clip = local_clip(n, rank, steps)
+            pin = (lambda t: t.pin_memory()) if pinned else (lambda t: t)
+            self.host = {k: pin(v) for k, v in clip.items() if isinstance(v, torch.Tensor)}
+            self.host_flow = pin(torch.cat(clip["flow"], dim=0))
+            self.host_inv = {t: pin(v) for t, v in clip["inversion"].items()}
+            self.dev = {k: v.to(device) for k, v in self.host.items()}
+            self.dev_flow = self.host_flow.to(device)
+            self.dev_inv = {t: v.to(device) for t, v in self.host_inv.items()}
+            self.kw = dict(test_model_kwargs=dict(inpaint_image=self.dev["inpaint_image"], inpaint_mask=self.dev["inpaint_mask"]))
+
+        def activate(self):
+            frame_shard.activate(self.shard)
+            sampler._register_hooks(self.dev_flow)
+            sampler._inv_cache = self.dev_inv
+
+        def step(self, i, x):
+            i = i % DDIM_STEPS
+            step = int(time_range[i])
+            ts = torch.full((self.n,), step, device=device, dtype=torch.long)
+            x_prev, _ = sampler.p_sample_ddim_with_inverse(
+                x, self.dev["c"], ts, index=DDIM_STEPS - 1 - i, target_conditioning=self.dev["target_cond"],
+                inverse_results_dir=self.dev_inv, unconditional_guidance_scale=CFG_SCALE,
+                unconditional_conditioning=self.dev["uc"], flow=self.dev_flow, _step=step, **self.kw)
+            return x_prev
+
+        def timed(self, warm, k, first=0):
+            """`warm` untimed then `k` timed steps; returns (ms of the k steps on this rank, last latents)."""
+            x = self.dev["x_T"]
+            with torch.no_grad():
+                for i in range(first, first + warm):
+                    x = self.step(i, x)
+                barrier()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for i in range(first + warm, first + warm + k):
+                    x = self.step(i, x)
+                e1.record()
+                barrier()
+            return e0.elapsed_time(e1), x
+
+    def max_over_ranks(v):
+        t = torch.tensor([float(v)], device=device, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item()
+
+    run = Runner(frames)
+    run.activate()
+    shard = run.shard
+    host, host_flow, host_inv = run.host, run.host_flow, run.host_inv
+    one_step = run.step
+
+    x = run.dev["x_T"]
     with torch.no_grad():
         for i in range(W):
             x = one_step(i, x)
@@ -302,40 +464,72 @@ def main():
         launches = ops.launch_count - launches0
         attn_ms = ops.profile_attention(None)
     ms_total = ev0.elapsed_time(ev1)
+
+    # ---- memory-bound kernels, timed live inside two more steps of the same loop (not inside the K timed steps: an event
+    # pair around each of ~230 launches per step would perturb the headline) --------------------------------------------
+    secondary = None
+    if not args.no_secondary:
+        ops.profile_kernels(True)
+        with torch.no_grad():
+            for i in range(W + K, W + K + 2):
+                x = one_step(i, x)
+        secondary = summarize_secondary(ops.profile_kernels(None), 2, peaks())
+        barrier()
+
     # secondary figure ("report throughput both ways"): the same steps with the output-dead recon
     # branch skipped (UNet batch 2 x frames).  Never the headline: `value` above is the faithful 3-branch step.
     elide_ms = None
     if not args.elide_recon and not args.no_elide_extra:
         sampler.elide_dead_recon = True
-        sampler._register_hooks(dev_flow)
-        with torch.no_grad():
-            xe = dev["x_T"]
-            for i in range(2):
-                xe = one_step(i, xe)
-            barrier()
-            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            f0.record()
-            for i in range(2, 2 + min(K, 5)):
-                xe = one_step(i, xe)
-            f1.record()
-            barrier()
-        elide_ms = f0.elapsed_time(f1) / min(K, 5)
+        run.activate()
+        ke = min(K, 5)
+        t_e, _ = run.timed(2, ke)
+        elide_ms = t_e / ke
         sampler.elide_dead_recon = False
-        sampler._register_hooks(dev_flow)
-    tmax = torch.tensor([ms_total], device=device, dtype=torch.float64)
+        run.activate()
     lsum = torch.tensor([float(launches)], device=device, dtype=torch.float64)
     if world > 1:
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         dist.all_reduce(lsum, op=dist.ReduceOp.SUM)
-    ms_per_step = tmax.item() / K
+    ms_per_step = max_over_ranks(ms_total) / K
     value = total_frames / (DDIM_STEPS * ms_per_step * 1e-3)
     elide = None
     if elide_ms is not None:
-        te = torch.tensor([elide_ms], device=device, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        elide = dict(value=total_frames / (DDIM_STEPS * te.item() * 1e-3), unit=UNIT, ms_per_step=te.item(), branches=2,
+        te = max_over_ranks(elide_ms)
+        elide = dict(value=total_frames / (DDIM_STEPS * te * 1e-3), unit=UNIT, ms_per_step=te, branches=2,
                      note="same step with the recon branch skipped: bit-identical samples (SURVEY.md F3), secondary figure only")
+
+    # ---- BASELINE.json configs[4] as written: ONE 256-frame clip split over the ranks (128 / 64 / 32 frames per rank at
+    # 2 / 4 / 8 GPUs; all 256 on one GPU at N=1), so that the driver's N = 1, 2, 4, 8 lines carry a STRONG-scaling series
+    # next to the weak-scaling headline.  Secondary figure; same step, same kernels. -------------------------------------
+    clip256 = None
+    if not strong and not args.no_clip256 and 256 % world == 0:
+        n256 = 256 // world
+        if n256 == frames:
+            clip256 = dict(total_frames=256, frames_per_gpu=n256, ms_per_step=ms_per_step, value=value, unit=UNIT,
+                           scaling="strong", note="identical to the headline run at this N")
+        else:
+            del x
+            torch.cuda.empty_cache()
+            r256 = Runner(n256, pinned=False)
+            r256.activate()
+            k256 = 3
+            t256, x256 = r256.timed(2, k256)
+            ms256 = max_over_ranks(t256) / k256
+            clip256 = dict(total_frames=256, frames_per_gpu=n256, ms_per_step=ms256, steps=k256, warmup=2,
+                           value=256 / (DDIM_STEPS * ms256 * 1e-3), unit=UNIT, scaling="strong",
+                           halo=dict(messages=r256.shard.halo_messages, bytes=r256.shard.halo_bytes) if world > 1 else None,
+                           note="one 256-frame clip split by contiguous frame chunk over the ranks; efficiency(N) = value(N) / (N * value(1)) "
+                                "with value(1) = this object in the N=1 line")
+            del r256, x256
+            torch.cuda.empty_cache()
+            run.activate()
+
+    # ---- sharded == unsharded on real ranks, bf16, a small clip; --verify-shard is the strict
+    # fp32 form ------------------------------------------------------------------------------------------------------------
+    shard_check = None
+    if world > 1:
+        shard_check = shard_vs_single(sampler, rank, world, device, frames_per_rank=2, ddim_steps=2)
+        run.activate()
 
     # ---- roofline of the dominant kernel (fused attention, N=4096) -------------------------------------
     pk = peaks()
@@ -405,7 +599,7 @@ def main():
         cores = os.cpu_count() or 1
         torch.set_num_threads(cores)
         sd32 = {k: v.float() for k, v in sd.items()}
-        cpu_frames = 2                     # two frames: the flow warp between them is part of the sample
+        cpu_frames = CPU_ARM_FRAMES        # two frames: the flow warp between them is part of the sample
         t_step, _ = cpu_step_seconds(sd32, cpu_frames, 1, 1)
         cpu = dict(value=cpu_frames / (DDIM_STEPS * t_step), unit=UNIT, cores=cores, kind="port",
                    sample=f"{cpu_frames} frames x 1 timed DDIM step after 1 warm-up step (UNet batch {3 * cpu_frames}, hooks on, "
@@ -414,10 +608,11 @@ def main():
 
     if rank == 0:
         line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=K, warmup=W, ms_per_step=ms_per_step,
-                    higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16", data="synthetic",
-                    config=workload_config(frames, world, n_branches),
-                    clocks=clock_info, e2e=e2e, gpu_launches=int(lsum.item()), roofline=roof, cpu_baseline=cpu,
-                    elide_dead_recon=elide,
+                    higher_is_better=True, scaling="strong" if strong else "weak", vs_baseline=None, dtype="bf16",
+                    data="synthetic", config=workload_config(frames, world, n_branches, strong),
+                    clocks=clock_info, e2e=e2e, gpu_launches=int(lsum.item()), roofline=roof,
+                    roofline_secondary=secondary, cpu_baseline=cpu, elide_dead_recon=elide, clip256=clip256,
+                    shard_check=shard_check,
                     halo=dict(messages=shard.halo_messages, bytes=shard.halo_bytes) if world > 1 else None)
         print(json.dumps(line), flush=True)
     if world > 1:

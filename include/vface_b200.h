@@ -13,6 +13,11 @@
  *   - return 0 on success, non-zero on failure with a message in
  *     vf_last_error() (thread-local);
  *   - there is no CPU fallback: without an sm_100a device the calls fail.
+ *   - one process drives ONE GPU: every launch goes to the CURRENT CUDA device, and
+ *     the library binds itself to the device that is current at the first call (its
+ *     function attributes, cuBLASLt handle/plans and grid sizes are per device).  A
+ *     later call with another device current fails with a message instead of
+ *     launching there.  Multi-GPU = one process per GPU (torch.distributed / torchrun).
  *   - dtype: VF_F32 is the fp32 reference-precision path, VF_BF16 the tensor-core
  *     path (bf16 storage, fp32 accumulation).
  *   - token tensors use the reference's native (batch, n, heads*d_head) layout;

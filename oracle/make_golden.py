@@ -232,6 +232,115 @@ def golden_sampler_full_s10():
     save("sampler_full_s10.npz", x_inter=torch.stack(inter["x_inter"][1:]).numpy())
 
 
+def golden_sampler_full_8f():
+    """BASELINE.json configs[0] at its full frame count: 8 frames, DDIM 10 steps, CFG 3.0, hooks on, the FULL-SIZE
+    UNet -- as the two B=4 windows SURVEY.md 8(d) allows (the reference materialises 24*B*4096^2 fp32 scores; the
+    smoothing window of the reference is the DataLoader batch, so frame 4 has no predecessor).  One 8-frame clip from
+    vface_b200.synth, frames [0,4) and [4,8); kept: the per-step latents of steps 1, 5 and 10 of each window."""
+    from vface_b200 import synth
+    from . import kernels as ok
+    ref = rh.build_reference_unet()
+    ref.load_state_dict(synth.synth_state_dict(ref.state_dict(), seed=1))
+    F, B, S = 8, 4, 10
+    steps = ok.make_schedule(S)["ddim_timesteps"]
+    clip = synth.synth_clip(F, steps=steps, flow_kind="smooth")
+    out = {}
+    for wi, lo in enumerate(range(0, F, B)):
+        hi = lo + B
+        sampler = rh.build_reference_sampler(ref)
+        d = tempfile.mkdtemp()
+        for t, v in clip["inversion"].items():
+            torch.save(v[lo:hi].clone(), os.path.join(d, f"ddim_latents_{t}.pt"))
+        with quiet():
+            samples, inter = sampler.sample(
+                S=S, batch_size=B, shape=(4, 64, 64), conditioning=clip["c"][lo:hi], target_conditioning=clip["target_cond"][lo:hi],
+                inverse_results_dir=d, x_T=clip["x_T"][lo:hi], flow=clip["flow"][lo:hi - 1], unconditional_guidance_scale=3.0,
+                unconditional_conditioning=clip["uc"][lo:hi], eta=0.0, verbose=False, log_every_t=1,
+                test_model_kwargs=dict(inpaint_image=clip["inpaint_image"][lo:hi], inpaint_mask=clip["inpaint_mask"][lo:hi]))
+        xs = torch.stack(inter["x_inter"][1:])
+        out[f"x_inter_w{wi}"] = xs[[0, 4, 9]].numpy()
+        print("window", wi, "done", flush=True)
+    out["kept_steps"] = np.array([0, 4, 9])
+    save("sampler_full_8f.npz", **out)
+
+
+def golden_sampler_small_2way():
+    """Row a4: DDIMSampler.p_sample_ddim (ddim_w_inv.py:564-617), the 2-way [uncond ; cond] step, on the reduced UNet.
+    (1) called directly on an un-hooked UNet for three consecutive steps of a DDIM-10 schedule;
+    (2) through sample(target_conditioning=None): ddim_sampling still registers the chunks=3 hooks (:289-305), which
+        then split the 2B batch into thirds -- B = 3 so that 2B divides by 3 (any other B makes combine_fft_high_low's
+        torch.cat fail in the reference); flow=None.  The mirror must reproduce that slicing, not 'fix' it."""
+    from vface_b200 import synth
+    from . import kernels as ok
+    ref = rh.build_reference_unet(SMALL_UNET)
+    ref.load_state_dict(synth.synth_state_dict(ref.state_dict(), seed=1))
+    S = 10
+    out = {}
+    # (1) direct calls, hooks never registered
+    B = 2
+    clip = synth.synth_clip(B)
+    sampler = rh.build_reference_sampler(ref)
+    with quiet():
+        sampler.make_schedule(S, ddim_eta=0.0, verbose=False)
+    x = clip["x_T"]
+    time_range = np.flip(sampler.ddim_timesteps)
+    xs, p0s = [], []
+    kw = dict(test_model_kwargs=dict(inpaint_image=clip["inpaint_image"], inpaint_mask=clip["inpaint_mask"]))
+    for i in range(3):
+        ts = torch.full((B,), int(time_range[i]), dtype=torch.long)
+        with quiet():
+            x, p0 = sampler.p_sample_ddim(x, clip["c"], ts, index=S - 1 - i, unconditional_guidance_scale=3.0,
+                                          unconditional_conditioning=clip["uc"], **kw)
+        xs.append(x)
+        p0s.append(p0)
+    out["direct_x_prev"] = torch.stack(xs).numpy()
+    out["direct_pred_x0"] = torch.stack(p0s).numpy()
+    # scale 1.0: the single-branch path (:577-578)
+    ts = torch.full((B,), int(time_range[0]), dtype=torch.long)
+    with quiet():
+        x1, _ = sampler.p_sample_ddim(clip["x_T"], clip["c"], ts, index=S - 1, unconditional_guidance_scale=1.0,
+                                      unconditional_conditioning=clip["uc"], **kw)
+    out["direct_x_prev_scale1"] = x1.numpy()
+    # (2) through sample(), hooks registered by ddim_sampling, B = 3
+    B = 3
+    clip = synth.synth_clip(B)
+    sampler = rh.build_reference_sampler(ref)
+    with quiet():
+        samples, inter = sampler.sample(
+            S=S, batch_size=B, shape=(4, 64, 64), conditioning=clip["c"], target_conditioning=None,
+            x_T=clip["x_T"], flow=None, unconditional_guidance_scale=3.0, unconditional_conditioning=clip["uc"],
+            eta=0.0, verbose=False, log_every_t=1,
+            test_model_kwargs=dict(inpaint_image=clip["inpaint_image"], inpaint_mask=clip["inpaint_mask"]))
+    out["sample_x_inter"] = torch.stack(inter["x_inter"][1:]).numpy()
+    save("sampler_small_2way.npz", **out)
+
+
+def golden_sampler_small_eta():
+    """Row a13: eta = 0.5 through the reference sampler on the reduced UNet.  noise_like (util.py:264-267) is called
+    TWICE per step (ddim_w_inv.py:697 and :704) on the global CPU generator, seeded here with 123: the first draw of a
+    step is the noise of x_prev, the second belongs to the discarded recon branch.  A mirror that draws once per step
+    (or in another order) consumes a different sub-sequence and cannot match these latents."""
+    from vface_b200 import synth
+    from . import kernels as ok
+    ref = rh.build_reference_unet(SMALL_UNET)
+    ref.load_state_dict(synth.synth_state_dict(ref.state_dict(), seed=1))
+    B, S = 2, 5
+    steps = ok.make_schedule(S)["ddim_timesteps"]
+    clip = synth.synth_clip(B, steps=steps)
+    sampler = rh.build_reference_sampler(ref)
+    d = tempfile.mkdtemp()
+    for t, v in clip["inversion"].items():
+        torch.save(v, os.path.join(d, f"ddim_latents_{t}.pt"))
+    torch.manual_seed(123)
+    with quiet():
+        samples, inter = sampler.sample(
+            S=S, batch_size=B, shape=(4, 64, 64), conditioning=clip["c"], target_conditioning=clip["target_cond"],
+            inverse_results_dir=d, x_T=clip["x_T"], flow=clip["flow"], unconditional_guidance_scale=3.0,
+            unconditional_conditioning=clip["uc"], eta=0.5, verbose=False, log_every_t=1,
+            test_model_kwargs=dict(inpaint_image=clip["inpaint_image"], inpaint_mask=clip["inpaint_mask"]))
+    save("sampler_small_eta.npz", x_inter=torch.stack(inter["x_inter"][1:]).numpy(), seed=np.array(123), eta=np.array(0.5))
+
+
 def golden_unet_full():
     """One forward of the full-size UNet (project_ffhq.yaml) on a 3-way batch of one frame."""
     from vface_b200 import synth
@@ -293,7 +402,7 @@ def main():
     if not rh.available():
         sys.exit("reference not mounted; golden vectors can only be generated in the build container")
     rh.install()
-    which = sys.argv[1:] or ["fsai", "warp", "attn_hooks", "schedule", "sampler_small", "unet_full", "sampler_full", "sampler_full_s10", "vae_decoder", "vae_encoder"]
+    which = sys.argv[1:] or ["fsai", "warp", "attn_hooks", "schedule", "sampler_small", "unet_full", "sampler_full", "sampler_full_s10", "sampler_full_8f", "sampler_small_2way", "sampler_small_eta", "vae_decoder", "vae_encoder"]
     for w in which:
         globals()["golden_" + w]()
 

@@ -158,7 +158,7 @@ def _halo_worker(rank, world, port, frames_total, ret):
         sh = FrameShard(rank, world, frames_total)
         xl = sh.take(x)
         fl = sh.local_flow(flow)
-        halo_q, halo_k = sh.exchange_halo(xl[-1], -xl[-1])
+        halo_q, halo_k = sh.exchange_halo_async(xl[-1], -xl[-1]).wait()     # synchronous on CPU tensors
         if rank == 0:
             assert halo_q is None and len(fl) == sh.frames - 1
             loc = ok.flow_warp_blend(xl.numpy(), fl.numpy(), 0.8, h, w)

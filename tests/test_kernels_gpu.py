@@ -337,6 +337,23 @@ def test_attention_full_size_vs_fp32_kernel():
     assert (got1.float() - 1.0).abs().max().item() < 1e-2
 
 
+@pytest.mark.parametrize("heads,d", [(2, 40), (8, 40)])
+def test_attention_full_size_vs_oracle(heads, d):
+    """The dominant shape against the ORACLE itself (numpy float64 einsum-softmax-einsum, oracle/kernels.py, which restates
+    pnp_utils.py:270-286): N = 4096 tokens, d_head 40, 2 heads with both batch entries checked in full and the real
+    8-head layout with one batch entry -- every output element, 2e-2 max-abs, no tolerance scaling."""
+    from vface_b200 import ops
+    rng = np.random.default_rng(4096 + heads)
+    b, n = (2, 4096) if heads == 2 else (1, 4096)
+    q, k, v = _attn_case(rng, b, n, n, heads, d, bf16=True)[:3]
+    want = ok.attention(q, k, v, heads, d ** -0.5)
+    t = lambda a: torch.from_numpy(a).to(_dev()).bfloat16()
+    got = ops.attention(t(q), t(k), t(v), heads).float().cpu().numpy()
+    err = np.abs(got - want).max()
+    assert err < BF16_TOL, err
+    assert np.abs(want).max() > 0.02 and err < 0.25 * np.abs(want).max()        # not a vacuous comparison
+
+
 def test_errors_are_loud():
     from vface_b200 import ops
     x = torch.zeros(1, 64, 44, device=_dev(), dtype=torch.bfloat16)

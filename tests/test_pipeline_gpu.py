@@ -220,3 +220,188 @@ def test_full_size_step_vs_oracle_port():
         unconditional_guidance_scale=3.0, unconditional_conditioning=g(clip["uc"]), flow=clip["flow"],
         test_model_kwargs=dict(inpaint_image=g(clip["inpaint_image"]), inpaint_mask=g(clip["inpaint_mask"])))
     assert rel_l2(x_prev, xs[0]) < 1e-2
+
+
+# ---- rows a4 / a13 / (b): the 2-way step, the RNG draws, the script's autocast ----------------------------
+def test_p_sample_ddim_direct_vs_reference_golden():
+    """Row a4: DDIMSampler.p_sample_ddim (ddim_w_inv.py:564-617), the 2-way [uncond ; cond] step, called directly for
+    three consecutive steps on an un-hooked reduced UNet, against the unmodified reference; plus its single-branch path
+    (unconditional_guidance_scale == 1, :577-578)."""
+    from vface_b200 import synth
+    gold = np.load(os.path.join(GOLD, "sampler_small_2way.npz"))
+    _, sampler, _ = build(SMALL, torch.float32)
+    S, B = 10, 2
+    clip = synth.synth_clip(B)
+    sampler.make_schedule(S, ddim_eta=0.0, verbose=False)
+    g = lambda t: t.cuda()
+    kw = dict(test_model_kwargs=dict(inpaint_image=g(clip["inpaint_image"]), inpaint_mask=g(clip["inpaint_mask"])))
+    time_range = np.flip(sampler.ddim_timesteps)
+    x = g(clip["x_T"])
+    for i in range(3):
+        ts = torch.full((B,), int(time_range[i]), device="cuda", dtype=torch.long)
+        x, p0 = sampler.p_sample_ddim(x, g(clip["c"]), ts, index=S - 1 - i, unconditional_guidance_scale=3.0,
+                                      unconditional_conditioning=g(clip["uc"]), **kw)
+        assert rel_l2(x, gold["direct_x_prev"][i]) < 2e-4, i
+        assert rel_l2(p0, gold["direct_pred_x0"][i]) < 2e-4, i
+    ts = torch.full((B,), int(time_range[0]), device="cuda", dtype=torch.long)
+    x1, _ = sampler.p_sample_ddim(g(clip["x_T"]), g(clip["c"]), ts, index=S - 1, unconditional_guidance_scale=1.0,
+                                  unconditional_conditioning=g(clip["uc"]), **kw)
+    assert rel_l2(x1, gold["direct_x_prev_scale1"]) < 2e-4
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-4), (torch.bfloat16, 1e-2)])
+def test_sample_without_target_conditioning_vs_reference_golden(dtype, tol):
+    """Row a4 through the public entry: sample(target_conditioning=None) dispatches to p_sample_ddim (:337-344) while
+    ddim_sampling has still registered the chunks=3 hooks (:289-305), which then cut the 2B batch into thirds
+    (pnp_utils.py:97-101).  B = 3 (the only kind of B the reference itself survives); the mirror reproduces the
+    reference's slicing, it does not 'fix' it."""
+    from vface_b200 import synth
+    gold = np.load(os.path.join(GOLD, "sampler_small_2way.npz"))
+    _, sampler, _ = build(SMALL, dtype)
+    S, B = 10, 3
+    clip = synth.synth_clip(B)
+    g = lambda t: t.cuda()
+    samples, inter = sampler.sample(
+        S=S, batch_size=B, shape=(4, 64, 64), conditioning=g(clip["c"]), target_conditioning=None, x_T=g(clip["x_T"]),
+        flow=None, unconditional_guidance_scale=3.0, unconditional_conditioning=g(clip["uc"]), eta=0.0, verbose=False,
+        log_every_t=1, test_model_kwargs=dict(inpaint_image=g(clip["inpaint_image"]), inpaint_mask=g(clip["inpaint_mask"])))
+    want = gold["sample_x_inter"]
+    errs = [rel_l2(inter["x_inter"][1 + i], want[i]) for i in range(S)]
+    assert max(errs) < tol, errs
+
+
+def test_eta_noise_two_draws_per_step_vs_reference_golden(monkeypatch):
+    """Row a13: the reference calls noise_like TWICE per step (ddim_w_inv.py:697 for x_prev, :704 for the discarded recon
+    branch).  tests/golden/sampler_small_eta.npz is the unmodified reference at eta = 0.5 with the global CPU generator
+    seeded 123; here noise_like is replaced by draws from a CPU generator with that seed, so the trajectories agree only
+    if the mirror consumes the same sub-sequence: two draws per step, the FIRST one used."""
+    from oracle import kernels as ok
+    from vface_b200 import synth
+    from vface_b200.ldm.models.diffusion import ddim_w_inv as mod
+    gold = np.load(os.path.join(GOLD, "sampler_small_eta.npz"))
+    gen = torch.Generator(device="cpu").manual_seed(int(gold["seed"]))
+    calls = []
+
+    def cpu_noise_like(shape, device, repeat=False):
+        assert not repeat
+        calls.append(tuple(shape))
+        return torch.randn(shape, generator=gen).to(device)
+
+    monkeypatch.setattr(mod, "noise_like", cpu_noise_like)
+    _, sampler, _ = build(SMALL, torch.float32)
+    S, B = 5, 2
+    clip = synth.synth_clip(B, steps=ok.make_schedule(S)["ddim_timesteps"])
+    g = lambda t: t.cuda()
+    samples, inter = sampler.sample(
+        S=S, batch_size=B, shape=(4, 64, 64), conditioning=g(clip["c"]), target_conditioning=g(clip["target_cond"]),
+        inverse_results_dir=clip["inversion"], x_T=g(clip["x_T"]), flow=clip["flow"], unconditional_guidance_scale=3.0,
+        unconditional_conditioning=g(clip["uc"]), eta=float(gold["eta"]), verbose=False, log_every_t=1,
+        test_model_kwargs=dict(inpaint_image=g(clip["inpaint_image"]), inpaint_mask=g(clip["inpaint_mask"])))
+    assert calls == [(B, 4, 64, 64)] * (2 * S)
+    errs = [rel_l2(inter["x_inter"][1 + i], gold["x_inter"][i]) for i in range(S)]
+    assert max(errs) < 2e-4, errs
+
+
+def test_noise_draws_advance_cuda_generator_twice_per_step():
+    """Row a13 on the real generator: after one p_sample_ddim_with_inverse step (eta > 0) the CUDA generator is where two
+    torch.randn(B, 4, 64, 64) draws leave it, and x_prev carries the FIRST draw:
+    x_prev - x_prev(eta-free part) = sigma_t * noise_1 (ddim_w_inv.py:696-700)."""
+    from oracle import kernels as ok
+    from vface_b200 import synth
+    _, sampler, _ = build(SMALL, torch.float32)
+    S, B = 5, 2
+    steps = ok.make_schedule(S)["ddim_timesteps"]
+    clip = synth.synth_clip(B, steps=steps)
+    g = lambda t: t.cuda()
+    sampler.make_schedule(S, ddim_eta=0.7, verbose=False)
+    sampler._register_hooks(clip["flow"])
+    step = int(steps[-1])
+    args = (g(clip["x_T"]), g(clip["c"]), torch.full((B,), step, device="cuda", dtype=torch.long))
+    kw = dict(index=S - 1, target_conditioning=g(clip["target_cond"]), inverse_results_dir={k: g(v) for k, v in clip["inversion"].items()},
+              unconditional_guidance_scale=3.0, unconditional_conditioning=g(clip["uc"]), flow=clip["flow"],
+              test_model_kwargs=dict(inpaint_image=g(clip["inpaint_image"]), inpaint_mask=g(clip["inpaint_mask"])))
+    torch.manual_seed(99)
+    x_prev, pred_x0 = sampler.p_sample_ddim_with_inverse(*args, **kw)
+    state_after_step = torch.cuda.get_rng_state()
+    torch.manual_seed(99)
+    n1 = torch.randn(B, 4, 64, 64, device="cuda")
+    _n2 = torch.randn(B, 4, 64, 64, device="cuda")
+    assert torch.equal(torch.cuda.get_rng_state(), state_after_step)
+    tb = sampler._host_tables
+    a_t, a_prev, sigma, s1m = (float(tb[k][S - 1]) for k in ("a_t", "a_prev", "sigma", "s1m"))
+    assert sigma > 0
+    e = (g(clip["x_T"]) - pred_x0 * a_t ** 0.5) / s1m
+    det = a_prev ** 0.5 * pred_x0 + (1.0 - a_prev - sigma ** 2) ** 0.5 * e
+    assert rel_l2(x_prev - det, sigma * n1) < 1e-3
+
+
+@pytest.mark.parametrize("start_dtype", [torch.float32, torch.bfloat16])
+def test_sampler_under_script_default_autocast(start_dtype):
+    """The drop-in target samples inside `with autocast("cuda")` by default (scripts/VFace_inference_batch.py:400,
+    :407-409; fp16).  With fp32 parameters the mirror adopts bf16 once, with bf16 parameters nothing changes; either way
+    autocast is off inside the mirrored forward (no float16 reaches a kernel) and every per-step latent stays within the
+    bf16 bound of the unmodified reference's."""
+    import warnings
+    from oracle import kernels as ok
+    from vface_b200 import synth
+    gold = np.load(os.path.join(GOLD, "sampler_small.npz"))
+    model, sampler, _ = build(SMALL, start_dtype)
+    S, B = 10, 2
+    clip = synth.synth_clip(B, steps=ok.make_schedule(S)["ddim_timesteps"], flow_kind="smooth")
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        with torch.autocast("cuda"):
+            samples, inter = run_sample(sampler, clip, S, B, clip["inversion"])
+    assert model.model.diffusion_model.dtype == torch.bfloat16
+    assert (start_dtype == torch.float32) == any("autocast" in str(x.message) for x in w)
+    assert samples.dtype == torch.float32
+    errs = [rel_l2(inter["x_inter"][1 + i], gold["x_inter_smooth"][i]) for i in range(S)]
+    assert max(errs) < 1e-2, errs
+
+
+def test_hooked_attention_under_autocast_direct_call():
+    """A foreign caller invoking the patched attn1.forward inside an autocast region (no UNetModel.forward around it):
+    the closure switches autocast off itself."""
+    from vface_b200.ldm.modules.attention import CrossAttention
+    from vface_b200.ldm.models.pnp_utils import register_spa_attn_injection
+    torch.manual_seed(0)
+    attn = CrossAttention(query_dim=320, heads=8, dim_head=40).cuda().to(torch.bfloat16)
+    blk = torch.nn.Module(); blk.attn1 = attn
+    unet = torch.nn.Module()
+    unet.input_blocks = torch.nn.ModuleList([blk]); unet.middle_block = torch.nn.ModuleList([]); unet.output_blocks = torch.nn.ModuleList([])
+
+    class H:
+        pass
+    h = H(); h.model = H(); h.model.model = H(); h.model.model.diffusion_model = unet
+    register_spa_attn_injection(h, 1, switch_on=True, input_blocks=True, output_blocks=False, middle_block=False,
+                                attn_component="attn1", chunks=3, fusion="fft", split_ratio_fft=0.8)
+    x = torch.randn(3, 256, 320, device="cuda", dtype=torch.bfloat16)
+    with torch.no_grad():
+        want = attn.forward(x.clone())
+        with torch.autocast("cuda"):
+            got = attn.forward(x.clone())
+    assert got.dtype == torch.bfloat16 and torch.equal(got, want)
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-4), (torch.bfloat16, 1e-2)])
+def test_config0_eight_frames_vs_reference_golden(dtype, tol):
+    """BASELINE.json configs[0] at its full frame count: 8-frame clip, DDIM 10 steps, CFG 3.0, hooks on, full-size UNet,
+    as the two B=4 windows SURVEY.md 8(d) allows (tests/golden/sampler_full_8f.npz: the unmodified reference on CPU,
+    per-step latents of steps 1, 5 and 10 of both windows).  The smoothing window of the reference is the batch, so each
+    window is one sample() call: frames [0,4) and [4,8) of one 8-frame synthetic clip."""
+    from oracle import kernels as ok
+    from vface_b200 import synth
+    gold = np.load(os.path.join(GOLD, "sampler_full_8f.npz"))
+    _, sampler, _ = build(None, dtype)
+    F, B, S = 8, 4, 10
+    clip = synth.synth_clip(F, steps=ok.make_schedule(S)["ddim_timesteps"], flow_kind="smooth")
+    kept = [int(i) for i in gold["kept_steps"]]
+    for wi, lo in enumerate(range(0, F, B)):
+        hi = lo + B
+        win = {k: v[lo:hi] for k, v in clip.items() if isinstance(v, torch.Tensor)}
+        win["flow"] = clip["flow"][lo:hi - 1]
+        inv = {t: v[lo:hi] for t, v in clip["inversion"].items()}
+        _, inter = run_sample(sampler, win, S, B, inv)
+        want = gold[f"x_inter_w{wi}"]
+        errs = [rel_l2(inter["x_inter"][1 + s], want[j]) for j, s in enumerate(kept)]
+        assert max(errs) < tol, (wi, errs)

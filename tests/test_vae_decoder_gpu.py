@@ -86,6 +86,33 @@ def test_decoded_frames_psnr_bf16_sampler_vs_reference(kind):
     assert p >= 40.0, p
 
 
+def test_decoded_frames_psnr_full_size_bf16_sampler_vs_reference():
+    """The same >= 40 dB bound on the FULL-SIZE path: the bf16 sampler over the 859.5 M-parameter UNet (DDIM 10 steps,
+    BASELINE.json configs[0] schedule, hooks on) against the unmodified reference's final latents
+    (tests/golden/sampler_full_s10.npz, last per-step latent = the samples), both decoded to 512x512 frames by the
+    full REFace first-stage decoder (ddconfig of project_ffhq.yaml: ch 128, mid attention width 512; random-init weights)."""
+    from oracle import kernels as ok
+    from tests.test_pipeline_gpu import build, run_sample
+    from vface_b200 import synth
+    gold = np.load(os.path.join(GOLD, "sampler_full_s10.npz"))
+    _, sampler, _ = build(None, torch.bfloat16)
+    S, B = 10, 2
+    clip = synth.synth_clip(B, steps=ok.make_schedule(S)["ddim_timesteps"], flow_kind="integer")
+    samples, _ = run_sample(sampler, clip, S, B, clip["inversion"])
+    del sampler
+    torch.cuda.empty_cache()
+    want = torch.from_numpy(gold["x_inter"][-1]).cuda()
+    dec = _decoder(torch.float32, None)                                   # REFACE_DDCONFIG: 64x64 latents -> 512x512 frames
+    with torch.no_grad():
+        a = dec.decode(samples.float() / 0.18215)
+        b = dec.decode(want / 0.18215)
+    assert tuple(a.shape) == (B, 3, 512, 512)
+    img = torch.clamp((b + 1) / 2, 0, 1)
+    assert 0.02 < img.std().item() and 0.05 < img.mean().item() < 0.95
+    p = psnr(a, b)
+    assert p >= 40.0, p
+
+
 # ---- encoder half (the save loop's encode -> decode round trip, scripts/VFace_inference_batch.py:456-459, :603-623) ----
 def _autoencoder(dtype, seed_dec=3, seed_enc=5):
     from vface_b200 import synth

@@ -25,12 +25,23 @@ _PATCHED_NAMES = {
     "ldm.modules.attention": ["CrossAttention", "BasicTransformerBlock", "SpatialTransformer", "FeedForward", "GEGLU"],
     "ldm.models.pnp_utils": ["register_spa_attn_injection", "find_all_modules_by_name"],
     "ldm.models.diffusion.ddim_w_inv": ["DDIMSampler", "load_ddim_latents_at_t"],
+    "ldm.modules.diffusionmodules.model": ["Decoder", "Encoder", "ResnetBlock", "AttnBlock", "Upsample", "Downsample"],
     "scripts.face_swap_utils": ["combine_fft_high_low"],
     "scripts.temporal_flow": ["align_by_flow", "warp_image"],
 }
 
-_SOURCES = dict(_MIRRORED, **{"scripts.face_swap_utils": "vface_b200.scripts.face_swap_utils",
+_SOURCES = dict(_MIRRORED, **{"ldm.modules.diffusionmodules.model": "vface_b200.ldm.modules.diffusionmodules.model",
+                              "scripts.face_swap_utils": "vface_b200.scripts.face_swap_utils",
                               "scripts.temporal_flow": "vface_b200.scripts.temporal_flow"})
+
+# Modules of the reference that bind mirrored names with `from X import name` at THEIR import time: if one of them is
+# already loaded when install() runs, its copy of the name is rebound too (module -> names it may hold).
+_IMPORTERS = {
+    "ldm.models.autoencoder": ["Encoder", "Decoder"],                                   # autoencoder.py:8
+    "ldm.models.diffusion.ddim_w_inv": ["register_spa_attn_injection"],                 # ddim_w_inv.py:17 (replaced wholesale anyway)
+    "ldm.models.pnp_utils": ["combine_fft_high_low", "align_by_flow"],
+    "ldm.modules.diffusionmodules.openaimodel": ["SpatialTransformer"],                 # openaimodel.py:20
+}
 
 
 def install(strict: bool = False):
@@ -52,6 +63,15 @@ def install(strict: bool = False):
         for n in names:
             setattr(ref_mod, n, getattr(mine, n))
             done.append((ref_name, n))
+    rebound = {n: obj for (m, n) in done for obj in [getattr(sys.modules[m], n)]}
+    for mod_name, names in _IMPORTERS.items():
+        mod = sys.modules.get(mod_name)
+        if mod is None or mod.__name__.startswith("vface_b200"):
+            continue
+        for n in names:
+            if n in rebound and hasattr(mod, n) and getattr(mod, n) is not rebound[n]:
+                setattr(mod, n, rebound[n])
+                done.append((mod_name, n))
     return done
 
 

@@ -17,4 +17,9 @@ int launch_attn_tc(const void* q, const void* k, const void* v, void* o, int bat
                    int d, long long ld_q, long long ld_k, long long ld_v, long long ld_o, float scale,
                    const void* k2, const void* v2, int n_kv2, long long ld_k2, long long ld_v2, cudaStream_t st);
 
+int launch_attn_stream(const void* q, const void* k, const void* v, void* o, int batch, int heads, int n_q, int n_kv,
+                       int d, long long ld_q, long long ld_k, long long ld_v, long long ld_o, float scale,
+                       const void* k2, const void* v2, int n_kv2, long long ld_k2, long long ld_v2, int emu,
+                       cudaStream_t st);
+
 }  // namespace vf

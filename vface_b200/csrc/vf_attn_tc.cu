@@ -553,7 +553,7 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 // (batch, n, heads*d) bf16 with row stride ld  ->  4-D map {d, heads, n, batch}, box {64, 1, rows, 1}.
-static int make_map(CUtensorMap* m, const void* base, int batch, int heads, int n, int d, long long ld, int box_rows) {
+int attn_make_map(CUtensorMap* m, const void* base, int batch, int heads, int n, int d, long long ld, int box_rows) {
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) return fail("vf_attn_fwd: cuTensorMapEncodeTiled entry point not found");
   cuuint64_t dims[4] = {(cuuint64_t)d, (cuuint64_t)heads, (cuuint64_t)n, (cuuint64_t)batch};
@@ -634,15 +634,25 @@ int launch_attn_tc(const void* q, const void* k, const void* v, void* o, int bat
     const char* e = getenv("VF_ATTN_LAGMAX");
     lag = e ? atoi(e) : 0;
   }
+  // VF_ATTN_STREAM: 1 (default) = the streamed-softmax arrangement of vf_attn_stream.cu for d_head <= 128 (S double-buffered
+  // in TMEM, two CTAs/SM); 0 = the arrangements below (kept for d_head in (128, 192] and for A/B measurements).
+  static int stream_mode = -1;
+  if (stream_mode < 0) {
+    const char* e = getenv("VF_ATTN_STREAM");
+    stream_mode = e ? atoi(e) : 1;
+  }
+  if (stream_mode && P.d_pad <= 128)
+    return launch_attn_stream(q, k, v, o, batch, heads, n_q, n_kv, d, ld_q, ld_k, ld_v, ld_o, scale, k2, v2, n_kv2, ld_k2, ld_v2,
+                              emu, st);
   const bool bn48 = split == 3 && P.d_pad <= 48;
   const int bn = bn48 ? 48 : 64;
   CUtensorMap mq, mk, mv, mk2, mv2;
-  if (int rc = make_map(&mq, q, batch, heads, n_q, d, ld_q, kBM)) return rc;
-  if (int rc = make_map(&mk, k, batch, heads, n_kv, d, ld_k, bn)) return rc;
-  if (int rc = make_map(&mv, v, batch, heads, n_kv, d, ld_v, bn)) return rc;
+  if (int rc = attn_make_map(&mq, q, batch, heads, n_q, d, ld_q, kBM)) return rc;
+  if (int rc = attn_make_map(&mk, k, batch, heads, n_kv, d, ld_k, bn)) return rc;
+  if (int rc = attn_make_map(&mv, v, batch, heads, n_kv, d, ld_v, bn)) return rc;
   if (has2) {
-    if (int rc = make_map(&mk2, k2, batch, heads, n_kv2, d, ld_k2, bn)) return rc;
-    if (int rc = make_map(&mv2, v2, batch, heads, n_kv2, d, ld_v2, bn)) return rc;
+    if (int rc = attn_make_map(&mk2, k2, batch, heads, n_kv2, d, ld_k2, bn)) return rc;
+    if (int rc = attn_make_map(&mv2, v2, batch, heads, n_kv2, d, ld_v2, bn)) return rc;
   } else {
     mk2 = mk;
     mv2 = mv;

@@ -154,6 +154,10 @@ extern "C" int vf_ddim_invert_step(const void* x, const void* e_uncond, const vo
   if (n <= 0 || (n & 3)) return fail("vf_ddim_invert_step: n=%lld must be a positive multiple of 4", n);
   if (dtype_e != VF_F32 && dtype_e != VF_BF16) return fail("vf_ddim_invert_step: bad dtype %d", dtype_e);
   if (!aligned16(x) || !aligned16(x_next)) return fail("vf_ddim_invert_step: pointers must be 16-byte aligned");
+  // eps is read with 16-byte (fp32) / 8-byte (bf16) vector loads
+  const uintptr_t emask = dtype_e == VF_F32 ? 15 : 7;
+  if ((reinterpret_cast<uintptr_t>(e_cond) & emask) || (e_uncond && (reinterpret_cast<uintptr_t>(e_uncond) & emask)))
+    return fail("vf_ddim_invert_step: e_cond/e_uncond must be %d-byte aligned", (int)emask + 1);
   InvScalars s;
   s.s1m_cur = sqrtf(1.0f - a_cur);
   s.sqrt_next = sqrtf(a_next);

@@ -92,7 +92,7 @@ static int set_batch(cublasLtMatrixLayout_t l, int batch, long long stride) {
 
 // batch > 1: `rows` rows per batch entry, entries contiguous (stride rows * ld), W shared, bias (batch, n).
 static int make_plan(LtPlan& P, long long rows, int k, int n, long long ld_x, long long ld_res, long long ld_out, int dtype,
-                     bool has_bias, size_t ws_bytes, int batch) {
+                     bool has_bias, size_t ws_bytes, int batch, uint32_t align) {
   const cudaDataType_t dt = dtype == VF_BF16 ? CUDA_R_16BF : CUDA_R_32F;
   VF_LT_TRY(g_api.MatmulDescCreate(&P.op, CUBLAS_COMPUTE_32F, CUDA_R_32F));
   // row-major out (rows, n) = x (rows, k) . W^T  <=>  column-major out^T (n, rows) = W (k, n)^T . x^T (k, rows)
@@ -122,6 +122,12 @@ static int make_plan(LtPlan& P, long long rows, int k, int n, long long ld_x, lo
   cublasLtMatmulPreference_t pref = nullptr;
   VF_LT_TRY(g_api.MatmulPreferenceCreate(&pref));
   VF_LT_TRY(g_api.MatmulPreferenceSetAttribute(pref, CUBLASLT_MATMUL_PREF_MAX_WORKSPACE_BYTES, &ws_bytes, sizeof(ws_bytes)));
+  // the heuristic assumes 256-byte aligned operands unless told otherwise; the entry point only asks for 16 bytes, so
+  // the alignment class of THIS call's pointers/strides (part of the plan key) bounds what the algorithm may assume
+  VF_LT_TRY(g_api.MatmulPreferenceSetAttribute(pref, CUBLASLT_MATMUL_PREF_MIN_ALIGNMENT_A_BYTES, &align, sizeof(align)));
+  VF_LT_TRY(g_api.MatmulPreferenceSetAttribute(pref, CUBLASLT_MATMUL_PREF_MIN_ALIGNMENT_B_BYTES, &align, sizeof(align)));
+  VF_LT_TRY(g_api.MatmulPreferenceSetAttribute(pref, CUBLASLT_MATMUL_PREF_MIN_ALIGNMENT_C_BYTES, &align, sizeof(align)));
+  VF_LT_TRY(g_api.MatmulPreferenceSetAttribute(pref, CUBLASLT_MATMUL_PREF_MIN_ALIGNMENT_D_BYTES, &align, sizeof(align)));
   cublasLtMatmulHeuristicResult_t res;
   int found = 0;
   cublasStatus_t s = g_api.MatmulAlgoGetHeuristic(g_lt, P.op, P.a, P.b, P.c, d, pref, 1, &res, &found);
@@ -151,16 +157,24 @@ static int linear_residual_impl(const void* x, const void* w, const void* bias, 
   if (out == residual) return fail("vf_linear_residual: out must not alias residual");
   if (workspace_bytes < 0 || (workspace_bytes > 0 && !workspace)) return fail("vf_linear_residual: bad workspace");
 
+  // alignment class: the largest power of two <= 256 dividing every operand address and every row/batch stride in bytes
+  const size_t esz = dtype == VF_BF16 ? 2 : 4;
+  uintptr_t bits = reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(residual) |
+                   reinterpret_cast<uintptr_t>(out) | (uintptr_t)(ld_x * esz) | (uintptr_t)(ld_res * esz) |
+                   (uintptr_t)(ld_out * esz) | (uintptr_t)((size_t)k * esz) | 256u;
+  if (bias) bits |= reinterpret_cast<uintptr_t>(bias);
+  if (bias && batch > 1) bits |= (uintptr_t)((size_t)n * esz);
+  const uint32_t align = (uint32_t)(bits & (~bits + 1));
   LtPlan plan;
   {
     std::lock_guard<std::mutex> lock(g_lt_mutex);
     if (int rc = load_lt_api()) return rc;
     if (!g_lt) VF_LT_TRY(g_api.Create(&g_lt));
-    const auto key = std::make_tuple(rows, k, n, ld_x, ld_res, ld_out, dtype * 2 + (bias ? 1 : 0), (int)(workspace_bytes >> 20), batch);
+    const auto key = std::make_tuple(rows, k, n, ld_x, ld_res, ld_out, dtype * 2 + (bias ? 1 : 0), (int)(workspace_bytes >> 20), batch + ((int)align << 16));
     auto it = g_plans.find(key);
     if (it == g_plans.end()) {
       LtPlan fresh;
-      if (int rc = make_plan(fresh, rows, k, n, ld_x, ld_res, ld_out, dtype, bias != nullptr, (size_t)workspace_bytes, batch)) return rc;
+      if (int rc = make_plan(fresh, rows, k, n, ld_x, ld_res, ld_out, dtype, bias != nullptr, (size_t)workspace_bytes, batch, align)) return rc;
       it = g_plans.emplace(key, fresh).first;
     }
     plan = it->second;

@@ -829,7 +829,7 @@ geglu_kernel(const T* __restrict__ h, T* __restrict__ out, long long rows, int k
 
 template <typename T>
 __global__ void __launch_bounds__(256)
-add_bias_kernel(const T* __restrict__ a, const T* __restrict__ b, const T* __restrict__ bias, T* __restrict__ out,
+add_bias_kernel(const T* a, const T* __restrict__ b, const T* __restrict__ bias, T* out,     // out may alias a (in place)
                 long long rows, int c, long long rows_per_bias) {
   constexpr int E = V16<T>::E;
   const int chunks = c / E;

@@ -33,6 +33,7 @@ class FrameShard:
         self.lo, self.hi = shard_bounds(total_frames, world_size)[rank]
         self.halo_messages = 0
         self.halo_bytes = 0
+        self._side = None                    # CUDA side stream of exchange_halo_async
 
     @property
     def frames(self) -> int:
@@ -74,6 +75,27 @@ class FrameShard:
             return None, None
         return recv[0], recv[1]
 
+    def exchange_halo_async(self, q_last: torch.Tensor, k_last: torch.Tensor) -> "_PendingHalo":
+        """exchange_halo without stalling the caller's stream: on CUDA the send/receive is issued on a side stream that
+        waits for what has been enqueued so far (the FSAI of the last frame); .wait() makes the caller's stream wait for
+        the received rows and returns (halo_q, halo_k) -- (None, None) on rank 0.  On CPU (gloo tests) it is synchronous."""
+        if self.world_size == 1 or not q_last.is_cuda:
+            return _PendingHalo(None, self.exchange_halo(q_last, k_last), None)
+        main = torch.cuda.current_stream(q_last.device)
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=q_last.device)
+        side = self._side
+        ready = torch.cuda.Event()
+        ready.record(main)
+        with torch.cuda.stream(side):
+            side.wait_event(ready)
+            q_last.record_stream(side)
+            k_last.record_stream(side)
+            halo = self.exchange_halo(q_last, k_last)
+            done = torch.cuda.Event()
+            done.record(side)
+        return _PendingHalo(main, halo, done)
+
     def _peer(self, group_rank: int) -> int:
         if self.group is None:
             return group_rank
@@ -95,6 +117,19 @@ def _all_gather_uneven(parts, local, shard: "FrameShard"):
         if r == shard.rank:
             buf.copy_(local)
         dist.broadcast(buf, shard._peer(r), group=shard.group)
+
+
+class _PendingHalo:
+    def __init__(self, main, halo, done):
+        self._main, self._halo, self._done = main, halo, done
+
+    def wait(self):
+        if self._done is not None:
+            self._main.wait_event(self._done)
+            for t in self._halo:
+                if t is not None:
+                    t.record_stream(self._main)       # allocated on the side stream, consumed on the caller's
+        return self._halo
 
 
 _current: Optional[FrameShard] = None

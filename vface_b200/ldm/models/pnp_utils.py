@@ -22,6 +22,7 @@ from __future__ import annotations
 import torch
 
 from ... import frame_shard, ops
+from ..._autocast import no_autocast
 
 FLOW_TOKENS = 4096          # reference gate `q.shape[1] == 4096` (pnp_utils.py:201): the 64x64 level
 FLOW_HW = 64
@@ -58,6 +59,7 @@ def register_spa_attn_injection(model, injection_schedule, switch_on=True, input
 
     def spa_attn_forward(self):
 
+        @no_autocast          # a caller's autocast region would turn the projections into float16 (vface_b200/_autocast.py)
         def forward(x, context=None, mask=None, feature_transfer=True):
             if mask is not None:
                 raise NotImplementedError("attention masks are not used on the VFace hot path")
@@ -96,17 +98,29 @@ def register_spa_attn_injection(model, injection_schedule, switch_on=True, input
                         ops.fsai_blend(donor_q, cond_q, split_ratio_fft, out=sq)
                         ops.fsai_blend(donor_k, cond_k, split_ratio_fft, out=sk)
                     if use_flow:
-                        halo_q = halo_k = None
                         shard = frame_shard.current()
-                        if shard is not None and shard.world_size > 1:
-                            halo_q, halo_k = shard.exchange_halo(sq[B - 1], sk[B - 1])
+                        sharded = shard is not None and shard.world_size > 1
                         n_flow = _flow_len(flow)
-                        want = B if halo_q is not None else B - 1
+                        want = B if (sharded and shard.rank > 0) else B - 1
                         if n_flow != want:
                             raise ValueError(f"flow has {n_flow} fields for {B} frames"
-                                             f"{' + halo' if halo_q is not None else ''}; expected {want}")
-                        ops.flow_warp_blend(sq, flow, alpha, FLOW_HW, FLOW_HW, prev_halo=halo_q, out=cond_q)
-                        ops.flow_warp_blend(sk, flow, alpha, FLOW_HW, FLOW_HW, prev_halo=halo_k, out=cond_k)
+                                             f"{' + halo' if want == B else ''}; expected {want}")
+                        if not sharded:
+                            ops.flow_warp_blend(sq, flow, alpha, FLOW_HW, FLOW_HW, out=cond_q)
+                            ops.flow_warp_blend(sk, flow, alpha, FLOW_HW, FLOW_HW, out=cond_k)
+                        else:
+                            # The halo (post-FSAI q/k of the previous rank's last frame) travels on a side stream as soon
+                            # as FSAI is done; meanwhile frames 1.. of this shard, which only need their local predecessor,
+                            # are warped on the compute stream.  Frame 0 is warped last, against the received halo.
+                            pending = shard.exchange_halo_async(sq[B - 1], sk[B - 1])
+                            fl = ops._as_flow(flow, sq.device)
+                            own = fl[1:] if shard.rank > 0 else fl
+                            ops.flow_warp_blend(sq, own, alpha, FLOW_HW, FLOW_HW, out=cond_q)
+                            ops.flow_warp_blend(sk, own, alpha, FLOW_HW, FLOW_HW, out=cond_k)
+                            halo_q, halo_k = pending.wait()
+                            if halo_q is not None:
+                                ops.flow_warp_blend(sq[:1], fl[:1], alpha, FLOW_HW, FLOW_HW, prev_halo=halo_q, out=cond_q[:1])
+                                ops.flow_warp_blend(sk[:1], fl[:1], alpha, FLOW_HW, FLOW_HW, prev_halo=halo_k, out=cond_k[:1])
             return self.project_out(self.attend(q, k, v))
 
         return forward

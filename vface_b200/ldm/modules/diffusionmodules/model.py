@@ -23,6 +23,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .... import ops
+from ...._autocast import no_autocast
 
 
 def Normalize(in_channels, num_groups=32):
@@ -164,7 +165,9 @@ class Decoder(nn.Module):
         self.norm_out = Normalize(block_in)
         self.conv_out = nn.Conv2d(block_in, out_ch, kernel_size=3, stride=1, padding=1)
 
+    @no_autocast            # the script decodes under autocast("cuda") (VFace_inference_batch.py:407, :596): see _autocast.py
     def forward(self, z):
+        z = z.to(self.conv_in.weight.dtype)
         if z.dtype == torch.float32:
             # reference-precision path: keep the cuDNN convolutions in true fp32 (no TF32)
             with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
@@ -234,7 +237,9 @@ class Encoder(nn.Module):
         self.norm_out = Normalize(block_in)
         self.conv_out = nn.Conv2d(block_in, 2 * z_channels if double_z else z_channels, kernel_size=3, stride=1, padding=1)
 
+    @no_autocast
     def forward(self, x):
+        x = x.to(self.conv_in.weight.dtype)
         if x.dtype == torch.float32:
             with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
                 return self._forward(x)
@@ -295,7 +300,9 @@ class AutoencoderKLDecoder(nn.Module):
         self.decoder = Decoder(**cfg)
         self.post_quant_conv = nn.Conv2d(embed_dim, cfg["z_channels"], 1)
 
+    @no_autocast
     def decode(self, z):
+        z = z.to(self.post_quant_conv.weight.dtype)
         if z.dtype == torch.float32:
             with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
                 return self.decoder(self.post_quant_conv(z))
@@ -316,7 +323,9 @@ class AutoencoderKL(AutoencoderKLDecoder):
         self.encoder = Encoder(**cfg)
         self.quant_conv = nn.Conv2d(2 * cfg["z_channels"], 2 * embed_dim, 1)
 
+    @no_autocast
     def encode(self, x):
+        x = x.to(self.quant_conv.weight.dtype)
         if x.dtype == torch.float32:
             with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
                 return DiagonalGaussianDistribution(self.quant_conv(self.encoder(x)))

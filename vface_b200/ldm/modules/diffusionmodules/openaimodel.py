@@ -21,6 +21,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .... import ops
+from ...._autocast import adopt_autocast_dtype, no_autocast
 from ..attention import SpatialTransformer
 from .util import normalization, timestep_embedding, zero_module
 
@@ -273,6 +274,14 @@ class UNetModel(nn.Module):
         """(N, in_channels, H, W), (N,) timesteps, (N, M, context_dim) -> (N, out_channels, H, W)."""
         if y is not None:
             raise NotImplementedError("class-conditional UNet is not used by the VFace configuration")
+        # scripts/VFace_inference_batch.py:400-409 samples under autocast("cuda") by default: fp32 parameters become
+        # bf16 once (the caller asked for 16-bit compute), and autocast itself stays off inside -- it would turn every
+        # F.linear / F.conv2d result into float16, which the kernels do not take (vface_b200/_autocast.py)
+        adopt_autocast_dtype(self, "UNetModel.forward")
+        return self._forward_no_autocast(x, timesteps, context, return_features)
+
+    @no_autocast
+    def _forward_no_autocast(self, x, timesteps, context, return_features):
         dt = self.dtype
         if dt == torch.float32:
             # reference-precision path: keep cuDNN convolutions in true fp32 (no TF32)

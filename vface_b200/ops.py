@@ -7,6 +7,7 @@ provider here; there is no eager/CPU fallback -- CPU tensors or a missing librar
 from __future__ import annotations
 
 import os
+import threading
 
 from typing import Optional, Sequence, Union
 
@@ -24,23 +25,44 @@ def _count(n=1):
     launch_count += n
 
 
-_attn_prof = None   # (min_tokens, [(start_event, end_event), ...]) while profiling
+# ---- live kernel timing (bench.py: `roofline` and `roofline_secondary`) -----------------------------------
+_prof = None        # None, or {"filter": callable(kind, meta) -> bool, "events": [(kind, work, unit, ev0, ev1)]}
+
+
+def profile_kernels(start=None, only=None):
+    """profile_kernels(True) starts recording a CUDA event pair (on the launching stream) around every C-ABI launch
+    whose op describes itself with _describe(); `only` = iterable of kind prefixes to restrict it.
+    profile_kernels(None) stops and returns {kind: [(ms, work, unit), ...]} -- work = ALGORITHMIC bytes or flops of
+    that launch, not measured traffic."""
+    global _prof
+    if start:
+        pre = tuple(only) if only else None
+        _prof = {"filter": (lambda k: True) if pre is None else (lambda k: k.startswith(pre)), "events": []}
+        return None
+    if _prof is None:
+        return {}
+    torch.cuda.synchronize()
+    out = {}
+    for kind, work, unit, a, b in _prof["events"]:
+        out.setdefault(kind, []).append((a.elapsed_time(b), work, unit))
+    _prof = None
+    return out
 
 
 def profile_attention(min_tokens):
-    """Live timing of the attention kernel for the roofline in bench.py: profile_attention(n) starts
-    recording CUDA events (on the launching stream) around every vf_attn_fwd launch with n_q >= n;
-    profile_attention(None) stops and returns the per-launch durations in ms."""
-    global _attn_prof
+    """Live timing of the attention kernel for the roofline in bench.py: profile_attention(n) starts recording around
+    every vf_attn_fwd launch with n_q >= n; profile_attention(None) stops and returns the per-launch durations in ms."""
     if min_tokens is not None:
-        _attn_prof = (int(min_tokens), [])
+        profile_kernels(True, only=[f"attn n>={int(min_tokens)}"])
+        _prof["attn_min"] = int(min_tokens)
         return None
-    if _attn_prof is None:
-        return []
-    torch.cuda.synchronize()
-    out = [a.elapsed_time(b) for a, b in _attn_prof[1]]
-    _attn_prof = None
-    return out
+    res = profile_kernels(None)
+    return [ms for v in res.values() for ms, _, _ in v]
+
+
+def _describe(kind: str, work: float, unit: str = "B"):
+    """Called by an op right before its C-ABI launch: what the launch is and its algorithmic work."""
+    _op.desc = (kind, float(work), unit)
 
 
 def _code(t: torch.Tensor) -> int:
@@ -48,13 +70,63 @@ def _code(t: torch.Tensor) -> int:
         return VF_F32
     if t.dtype == torch.bfloat16:
         return VF_BF16
-    raise TypeError(f"vface_b200 kernels take float32 or bfloat16 tensors, got {t.dtype}")
+    hint = ""
+    if t.dtype == torch.float16:
+        hint = (" (float16 usually means a torch op ran under torch.autocast: the mirrored modules switch autocast off "
+                "inside their forward; wrap foreign callers in torch.autocast('cuda', enabled=False))")
+    raise TypeError(f"vface_b200 kernels take float32 or bfloat16 tensors, got {t.dtype}{hint}")
+
+
+_op = threading.local()     # device index of the operands of the op being issued (set by _need_cuda)
 
 
 def _need_cuda(*ts):
+    """Every operand on ONE CUDA device; that device is what the C-ABI call will run on (see _Lib)."""
+    dev = None
     for t in ts:
-        if t is not None and not t.is_cuda:
+        if t is None:
+            continue
+        if not t.is_cuda:
             raise RuntimeError("vface_b200 ops need CUDA tensors: there is no CPU fallback")
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise RuntimeError(f"vface_b200 ops need all operands on one device, got {dev} and {t.device}")
+    _op.index = dev.index if dev is not None else None
+
+
+class _Lib:
+    """The C-ABI entry points, called with the operands' device current.
+
+    The C side launches on the CURRENT device (and validates it: one process drives one GPU, include/vface_b200.h),
+    while the stream handed over belongs to the operands' device; a tensor on cuda:1 while cuda:0 is current would
+    otherwise launch on the wrong device with a foreign stream."""
+
+    def __getattr__(self, name):
+        fn = getattr(_lib.load(), name)
+
+        def call(*args):
+            idx = getattr(_op, "index", None)
+            if idx is not None and idx != torch.cuda.current_device():
+                with torch.cuda.device(idx):
+                    return call(*args)
+            desc = getattr(_op, "desc", None)
+            if desc is not None:
+                _op.desc = None
+                if _prof is not None and _prof["filter"](desc[0]):
+                    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    ev0.record()
+                    rc = fn(*args)
+                    ev1.record()
+                    _prof["events"].append((desc[0], desc[1], desc[2], ev0, ev1))
+                    return rc
+            return fn(*args)
+
+        setattr(self, name, call)        # resolved once per symbol
+        return call
+
+
+_LIB = _Lib()
 
 
 def _stream(t: torch.Tensor) -> int:
@@ -100,17 +172,14 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, sca
         if (b2, c2) != (b, c) or (b3, n3, c3) != (b, n_kv2, c) or k2.dtype != q.dtype or v2.dtype != q.dtype:
             raise ValueError("attention: bad k2/v2")
         p_k2, p_v2 = k2.data_ptr(), v2.data_ptr()
-    lib = _lib.load()
-    prof = _attn_prof is not None and n_q >= _attn_prof[0]
-    if prof:
-        ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-        ev[0].record()
+    lib = _LIB
+    tag = ""
+    if _prof is not None and n_q >= _prof.get("attn_min", 1 << 60):
+        tag = f"attn n>={_prof['attn_min']}"
+    _describe(tag or f"attn n={n_q} h={heads} d={d}", 4.0 * n_q * (n_kv + n_kv2) * d * heads * b, "flop")
     rc = lib.vf_attn_fwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), b, heads, n_q, n_kv, d,
                          ld_q, ld_k, ld_v, ld_o, float(scale), p_k2, p_v2, n_kv2, ld_k2, ld_v2,
                          _code(q), _stream(q))
-    if prof:
-        ev[1].record()
-        _attn_prof[1].append(ev)
     _lib.check(rc, "vf_attn_fwd")
     _count()
     return out
@@ -131,7 +200,8 @@ def fsai_blend(donor: torch.Tensor, dst: torch.Tensor, split_ratio: float = 0.8,
     if (b3, n3, d3) != (b, n, d) or out.dtype != dst.dtype:
         raise ValueError("fsai_blend: bad out tensor")
     split = int(d * split_ratio)
-    lib = _lib.load()
+    lib = _LIB
+    _describe(f"fsai_blend d={d}", 3.0 * b * n * d * dst.element_size())
     rc = lib.vf_fsai_blend(donor.data_ptr(), dst.data_ptr(), out.data_ptr(), b * n, d, split,
                            ld_d, ld_s, ld_o, _code(dst), _stream(dst))
     _lib.check(rc, "vf_fsai_blend")
@@ -154,7 +224,8 @@ def fsai_blend2(donor: torch.Tensor, dst_a: torch.Tensor, dst_b: torch.Tensor, s
             raise ValueError(f"fsai_blend2: {name} mismatch")
         lds.append(ld)
     split = int(d * split_ratio)
-    lib = _lib.load()
+    lib = _LIB
+    _describe(f"fsai_blend2 d={d}", 5.0 * b * n * d * donor.element_size())
     rc = lib.vf_fsai_blend2(donor.data_ptr(), dst_a.data_ptr(), out_a.data_ptr(), dst_b.data_ptr(), out_b.data_ptr(),
                             b * n, d, split, ld_d, lds[0], lds[1], lds[2], lds[3], _code(donor), _stream(donor))
     _lib.check(rc, "vf_fsai_blend2")
@@ -199,7 +270,8 @@ def flow_warp_blend(x: torch.Tensor, flow, alpha: float, h: int, w: int,
     taps = None
     if return_taps:
         taps = torch.empty((max(n_flow, 1), n, 2), dtype=torch.int32, device=x.device)
-    lib = _lib.load()
+    lib = _LIB
+    _describe(f"flow_warp c={c} hw={h}x{w}", (3.0 * n_flow + 2.0 * (frames - n_flow)) * n * c * x.element_size() + 8.0 * n * n_flow)
     rc = lib.vf_flow_warp_blend(x.data_ptr(), p_h, fl.data_ptr() if fl is not None else None, out.data_ptr(),
                                 frames, h, w, c, ld_x, ld_h, ld_o, float(alpha), _code(x),
                                 taps.data_ptr() if taps is not None else None, _stream(x))
@@ -223,7 +295,8 @@ def ddim_cfg_step(x: torch.Tensor, e_uncond: torch.Tensor, e_cond: torch.Tensor,
         raise ValueError("ddim_cfg_step: noise must be contiguous float32 of x's size")
     x_prev = torch.empty_like(x)
     pred_x0 = torch.empty_like(x)
-    lib = _lib.load()
+    lib = _LIB
+    _describe("ddim_cfg_step", x.numel() * (3.0 * 4 + 2.0 * e_cond.element_size() + (4.0 if noise is not None else 0.0)))
     rc = lib.vf_ddim_cfg_step(x.data_ptr(), e_uncond.data_ptr(), e_cond.data_ptr(), x_prev.data_ptr(), pred_x0.data_ptr(),
                               float(a_t), float(a_prev), float(sigma_t), float(sqrt_one_minus_at), float(cfg_scale),
                               noise.data_ptr() if noise is not None else None, x.numel(), _code(e_cond), _stream(x))
@@ -241,7 +314,7 @@ def ddim_invert_step(x: torch.Tensor, e_cond: torch.Tensor, a_cur: float, a_next
     if e_uncond is not None and (not e_uncond.is_contiguous() or e_uncond.dtype != e_cond.dtype or e_uncond.numel() != x.numel()):
         raise ValueError("ddim_invert_step: bad e_uncond")
     x_next = torch.empty_like(x)
-    lib = _lib.load()
+    lib = _LIB
     rc = lib.vf_ddim_invert_step(x.data_ptr(), e_uncond.data_ptr() if e_uncond is not None else None, e_cond.data_ptr(),
                                  x_next.data_ptr(), float(a_cur), float(a_next), float(cfg_scale), x.numel(),
                                  _code(e_cond), _stream(x))
@@ -280,9 +353,10 @@ def group_norm_nhwc(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, e
     if weight.dtype != x.dtype or bias.dtype != x.dtype or weight.numel() != c or bias.numel() != c or \
             (add_nc is not None and (add_nc.dtype != x.dtype or tuple(add_nc.shape) != (n, c))):
         raise ValueError("group_norm_nhwc: parameter dtype/shape mismatch")
-    lib = _lib.load()
+    lib = _LIB
     ws = torch.empty(lib.vf_group_norm_workspace_floats(n, hw, groups), dtype=torch.float32, device=x.device)
     y = torch.empty(x.shape[:-1] + (c,), dtype=x.dtype, device=x.device)
+    _describe(f"group_norm c={c}" + ("+silu" if silu else ""), 3.0 * n * hw * c * x.element_size())
     rc = lib.vf_group_norm_nhwc_cat(x.data_ptr(), c1, x2.data_ptr() if x2 is not None else None, c2,
                                     add_nc.contiguous().data_ptr() if add_nc is not None else None,
                                     weight.data_ptr(), bias.data_ptr(), y.data_ptr(), ws.data_ptr(), n, hw, groups,
@@ -313,7 +387,8 @@ def add_layer_norm(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, ep
     fused = y is not None or row_bias is not None
     res = torch.empty_like(x) if fused else None
     out = torch.empty_like(x)
-    lib = _lib.load()
+    lib = _LIB
+    _describe(f"layer_norm c={c}" + ("+add" if fused else ""), (2.0 + (1.0 if y is not None else 0.0) + (1.0 if fused else 0.0)) * rows * c * x.element_size())
     rc = lib.vf_add_layer_norm(x.data_ptr(), y.data_ptr() if y is not None else None,
                                row_bias.data_ptr() if row_bias is not None else None, rpb, weight.data_ptr(), bias.data_ptr(),
                                res.data_ptr() if fused else None, out.data_ptr(), rows, c, float(eps), _code(x), _stream(x))
@@ -328,7 +403,8 @@ def geglu(h: torch.Tensor) -> torch.Tensor:
     rows, two_k = _rows_c(h, "h")
     k = two_k // 2
     out = torch.empty(h.shape[:-1] + (k,), dtype=h.dtype, device=h.device)
-    lib = _lib.load()
+    lib = _LIB
+    _describe(f"geglu k={k}", 3.0 * rows * k * h.element_size())
     rc = lib.vf_geglu(h.data_ptr(), out.data_ptr(), rows, k, two_k, _code(h), _stream(h))
     _lib.check(rc, "vf_geglu")
     _count()
@@ -354,7 +430,8 @@ def linear_geglu(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Ten
     if bias is not None and (bias.dtype != x.dtype or bias.numel() != two_n or not bias.is_contiguous()):
         raise ValueError("linear_geglu: bad bias")
     out = torch.empty(x.shape[:-1] + (n,), dtype=x.dtype, device=x.device)
-    lib = _lib.load()
+    lib = _LIB
+    _describe(f"linear_geglu k={k} n={n}", 2.0 * rows * k * two_n, "flop")
     rc = lib.vf_linear_geglu(x.data_ptr(), weight.data_ptr(), bias.data_ptr() if bias is not None else None, out.data_ptr(),
                              rows, k, n, k, _code(x), _stream(x))
     _lib.check(rc, "vf_linear_geglu")
@@ -369,7 +446,8 @@ def upsample_nearest2x(x: torch.Tensor) -> torch.Tensor:
     n, c, h, w = x.shape
     xt = x.permute(0, 2, 3, 1).contiguous()
     out = torch.empty((n, 2 * h, 2 * w, c), dtype=x.dtype, device=x.device)
-    lib = _lib.load()
+    lib = _LIB
+    _describe(f"upsample2x c={c}", 5.0 * n * h * w * c * x.element_size())
     rc = lib.vf_upsample_nearest2x_nhwc(xt.data_ptr(), out.data_ptr(), n, h, w, c, _code(x), _stream(x))
     _lib.check(rc, "vf_upsample_nearest2x_nhwc")
     _count()
@@ -411,7 +489,7 @@ def linear_residual(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.
     ws = _lt_workspace.get(x.device)
     if ws is None:
         ws = _lt_workspace[x.device] = torch.empty(32 << 20, dtype=torch.uint8, device=x.device)
-    lib = _lib.load()
+    lib = _LIB
     if bias is not None and bias.dim() == 2:
         if x.dim() != 3 or bias.shape != (x.shape[0], n) or not bias.is_contiguous():
             raise ValueError("linear_residual: a per-batch bias needs x (batch, rows, k) and bias (batch, n)")
@@ -442,7 +520,8 @@ def conv3x3_out_f32(x_nhwc: torch.Tensor, conv) -> torch.Tensor:
     wt = conv.weight.detach().contiguous()                         # OIHW (tiny: 4 x c x 9)
     bias = conv.bias.detach().contiguous() if conv.bias is not None else None
     out = torch.empty((n, wt.shape[0], h, w), dtype=torch.float32, device=x_nhwc.device)
-    lib = _lib.load()
+    lib = _LIB
+    _describe(f"conv3x3_out c={c}", n * h * w * (c * 2.0 + wt.shape[0] * 4.0))
     rc = lib.vf_conv3x3_out_f32(x_nhwc.data_ptr(), wt.data_ptr(), bias.data_ptr() if bias is not None else None,
                                 out.data_ptr(), n, h, w, c, wt.shape[0], _code(x_nhwc), _stream(x_nhwc))
     _lib.check(rc, "vf_conv3x3_out_f32")
@@ -464,12 +543,15 @@ def add_bias(a: torch.Tensor, b: Optional[torch.Tensor] = None, row_bias: Option
             raise ValueError("add_bias: bad row_bias")
         nb = row_bias.numel() // c
         if nb > 1:
+            if rows % nb:
+                raise ValueError("add_bias: rows not divisible by bias rows")
             rpb = rows // nb
     if out is None:
         out = torch.empty_like(a)
     elif out.shape != a.shape or out.dtype != a.dtype or not out.is_contiguous():
         raise ValueError("add_bias: out must match a and be contiguous")
-    lib = _lib.load()
+    lib = _LIB
+    _describe(f"add_bias c={c}", (2.0 + (1.0 if b is not None else 0.0)) * rows * c * a.element_size())
     rc = lib.vf_add_bias(a.data_ptr(), b.data_ptr() if b is not None else None,
                          row_bias.data_ptr() if row_bias is not None else None, rpb, out.data_ptr(), rows, c, _code(a), _stream(a))
     _lib.check(rc, "vf_add_bias")
