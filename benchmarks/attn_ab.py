@@ -81,6 +81,8 @@ def main():
               ("N=64 h=8 d=160 frames=96", 96, 64, 8, 160)]
     if quick:
         tcases = tcases[:1]
+    if "--no-timing" in sys.argv:
+        tcases = []
     for name, b, n, h, d in tcases:
         q, k, v = mk(b, n, h * d), mk(b, n, h * d), mk(b, n, h * d)
         out = torch.empty_like(q)

@@ -377,6 +377,29 @@ def golden_vae_decoder():
     save("vae_decoder.npz", z=z.numpy(), out=y.numpy(), keys=np.array(sorted(sd.keys())))
 
 
+def golden_vae_decoder_full():
+    """The FULL first-stage decoder of the REFace config (project_ffhq.yaml first_stage_config.params.ddconfig: ch 128,
+    ch_mult 1-2-4-4, mid AttnBlock = one head of width 512 over 64 x 64 = 4096 tokens) + post_quant_conv, unmodified
+    reference on CPU, weights from vface_b200.synth (seed 3): one 64 x 64 latent -> 512 x 512 frame.  Kept: every 4th pixel
+    of the frame (3 x 128 x 128) and the first 8 latent rows' worth of input is regenerated from the seed by the test."""
+    from ldm.modules.diffusionmodules.model import Decoder
+    from vface_b200 import synth
+    full = dict(double_z=True, z_channels=4, resolution=256, in_channels=3, out_ch=3, ch=128, ch_mult=[1, 2, 4, 4],
+                num_res_blocks=2, attn_resolutions=[], dropout=0.0)
+    with quiet():
+        dec = Decoder(**full).eval()
+    pq = torch.nn.Conv2d(4, 4, 1)
+    sd = synth.synth_state_dict({**{"decoder." + k: v for k, v in dec.state_dict().items()},
+                                 **{"post_quant_conv." + k: v for k, v in pq.state_dict().items()}}, seed=3)
+    dec.load_state_dict({k[len("decoder."):]: v for k, v in sd.items() if k.startswith("decoder.")})
+    pq.load_state_dict({k[len("post_quant_conv."):]: v for k, v in sd.items() if k.startswith("post_quant_conv.")})
+    z = torch.randn(1, 4, 64, 64, generator=torch.Generator().manual_seed(23))
+    with torch.no_grad():
+        y = dec(pq(z / 0.18215))
+    save("vae_decoder_full.npz", out_strided=y[:, :, ::4, ::4].numpy(), out_mean=np.array(float(y.mean())),
+         out_std=np.array(float(y.std())), seed=np.array(23))
+
+
 def golden_vae_encoder():
     """Reference first-stage Encoder (model.py:368-459) + quant_conv (autoencoder.py:304, :322-326) on the reduced
     ddconfig, weights from vface_b200.synth (seed 5): image -> posterior moments; plus the posterior's mean / std."""
@@ -402,7 +425,7 @@ def main():
     if not rh.available():
         sys.exit("reference not mounted; golden vectors can only be generated in the build container")
     rh.install()
-    which = sys.argv[1:] or ["fsai", "warp", "attn_hooks", "schedule", "sampler_small", "unet_full", "sampler_full", "sampler_full_s10", "sampler_full_8f", "sampler_small_2way", "sampler_small_eta", "vae_decoder", "vae_encoder"]
+    which = sys.argv[1:] or ["fsai", "warp", "attn_hooks", "schedule", "sampler_small", "unet_full", "sampler_full", "sampler_full_s10", "sampler_full_8f", "sampler_small_2way", "sampler_small_eta", "vae_decoder", "vae_decoder_full", "vae_encoder"]
     for w in which:
         globals()["golden_" + w]()
 

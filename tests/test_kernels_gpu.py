@@ -354,6 +354,34 @@ def test_attention_full_size_vs_oracle(heads, d):
     assert np.abs(want).max() > 0.02 and err < 0.25 * np.abs(want).max()        # not a vacuous comparison
 
 
+@pytest.mark.parametrize("b,n_q,n_kv,heads,d", [(1, 1024, 1024, 1, 512), (2, 300, 200, 1, 512), (1, 256, 320, 2, 256), (1, 128, 64, 1, 384)])
+def test_attention_wide_head_vs_oracle(b, n_q, n_kv, heads, d):
+    """Wide heads (the first-stage AttnBlock is ONE head of width 512, ldm/modules/diffusionmodules/model.py:150-203): the
+    scores reduce over all d columns, the grid walks 128-wide column slices of V / O.  Against the oracle; the reference
+    scale of that block is c^-0.5 (model.py:178)."""
+    from vface_b200 import ops
+    rng = np.random.default_rng(d + n_q)
+    q, k, v = _attn_case(rng, b, n_q, n_kv, heads, d, bf16=True)[:3]
+    want = ok.attention(q, k, v, heads, d ** -0.5)
+    t = lambda a: torch.from_numpy(a).to(_dev()).bfloat16()
+    got = ops.attention(t(q), t(k), t(v), heads, scale=d ** -0.5).float().cpu().numpy()
+    err = np.abs(got - want).max()
+    assert err < BF16_TOL, err
+
+
+def test_attention_streamed_arrangement_env_knob():
+    """The streamed-softmax arrangement (csrc/vf_attn_stream.cu) for d_head <= 64 is an opt-in (VF_ATTN_STREAM=1, read once
+    per process): run it in a fresh interpreter against the fp32 kernel, incl. the exact-path and deferred-rescale cases."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, VF_ATTN_STREAM="1")
+    res = subprocess.run([sys.executable, os.path.join(root, "benchmarks", "attn_ab.py"), "--quick", "--no-timing"],
+                         capture_output=True, text=True, env=env, timeout=600, cwd=root)
+    assert res.returncode == 0 and "ATTN_AB_OK" in res.stdout, res.stdout[-3000:] + res.stderr[-2000:]
+
+
 def test_errors_are_loud():
     from vface_b200 import ops
     x = torch.zeros(1, 64, 44, device=_dev(), dtype=torch.bfloat16)

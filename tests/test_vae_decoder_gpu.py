@@ -86,6 +86,27 @@ def test_decoded_frames_psnr_bf16_sampler_vs_reference(kind):
     assert p >= 40.0, p
 
 
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-4), (torch.bfloat16, 3e-2)])
+def test_full_ddconfig_decoder_vs_reference_golden(dtype, tol):
+    """The FULL REFace first-stage decoder (ddconfig of project_ffhq.yaml: ch 128, mid AttnBlock = one head of width 512 over
+    4096 tokens) against the unmodified reference run on CPU (tests/golden/vae_decoder_full.npz: every 4th pixel of the
+    512 x 512 frame).  In bf16 the AttnBlock runs on the repo's own tcgen05 attention kernel (wide-head form)."""
+    from vface_b200 import ops
+    gold = np.load(os.path.join(GOLD, "vae_decoder_full.npz"))
+    m = _decoder(dtype, None)
+    z = torch.randn(1, 4, 64, 64, generator=torch.Generator().manual_seed(int(gold["seed"]))).cuda()
+    n0 = ops.launch_count
+    with torch.no_grad():
+        y = m.decode((z / 0.18215).to(dtype)).float()
+    assert tuple(y.shape) == (1, 3, 512, 512)
+    want = torch.from_numpy(gold["out_strided"]).cuda()
+    got = y[:, :, ::4, ::4]
+    err = ((got - want).norm() / want.norm()).item()
+    assert err < tol, err
+    assert abs(y.mean().item() - float(gold["out_mean"])) < 5e-2 * max(1.0, float(gold["out_std"]))
+    assert ops.launch_count > n0
+
+
 def test_decoded_frames_psnr_full_size_bf16_sampler_vs_reference():
     """The same >= 40 dB bound on the FULL-SIZE path: the bf16 sampler over the 859.5 M-parameter UNet (DDIM 10 steps,
     BASELINE.json configs[0] schedule, hooks on) against the unmodified reference's final latents

@@ -584,7 +584,8 @@ static int launch_tc(const CUtensorMap& mq, const CUtensorMap& mk, const CUtenso
 int launch_attn_tc(const void* q, const void* k, const void* v, void* o, int batch, int heads, int n_q, int n_kv,
                    int d, long long ld_q, long long ld_k, long long ld_v, long long ld_o, float scale,
                    const void* k2, const void* v2, int n_kv2, long long ld_k2, long long ld_v2, cudaStream_t st) {
-  if (d % 8 || d < 8 || d > 192) return fail("vf_attn_fwd(bf16): d_head=%d must be a multiple of 8 in [8, 192]", d);
+  if (d % 8 || d < 8 || (d > 192 && (d % 128 || d > 512)))
+    return fail("vf_attn_fwd(bf16): d_head=%d must be a multiple of 8 in [8, 192], or 256 / 384 / 512", d);
   const long long lds[4] = {ld_q, ld_k, ld_v, ld_o};
   for (long long ld : lds)
     if (ld % 8 || ld < (long long)heads * d) return fail("vf_attn_fwd(bf16): row strides must be multiples of 8 elements and >= heads*d");
@@ -634,14 +635,17 @@ int launch_attn_tc(const void* q, const void* k, const void* v, void* o, int bat
     const char* e = getenv("VF_ATTN_LAGMAX");
     lag = e ? atoi(e) : 0;
   }
-  // VF_ATTN_STREAM: 1 (default) = the streamed-softmax arrangement of vf_attn_stream.cu for d_head <= 128 (S double-buffered
-  // in TMEM, two CTAs/SM); 0 = the arrangements below (kept for d_head in (128, 192] and for A/B measurements).
+  // VF_ATTN_STREAM: 0 (default) = the arrangements below for d_head <= 192, and the streamed-softmax arrangement of
+  // vf_attn_stream.cu only for wide heads (d_head 256 / 384 / 512, which nothing else here can hold); 1 = streamed
+  // arrangement also for d_head <= 64 (S triple-buffered in TMEM, two CTAs/SM); 2 = also for d_head <= 128.  Measured at
+  // N = 4096, 8 x d40, 96 frame-branches (profiles/r2_attn_stream_ab.txt): 491-499 TF/s for the default against 428-451
+  // for the streamed one -- with 8 softmax warps per SM instead of 12 its XU pipe sits at 60 %.
   static int stream_mode = -1;
   if (stream_mode < 0) {
     const char* e = getenv("VF_ATTN_STREAM");
-    stream_mode = e ? atoi(e) : 1;
+    stream_mode = e ? atoi(e) : 0;
   }
-  if (stream_mode && P.d_pad <= 128)
+  if (d > 192 || (stream_mode && P.d_pad <= (stream_mode >= 2 ? 128 : 64)))
     return launch_attn_stream(q, k, v, o, batch, heads, n_q, n_kv, d, ld_q, ld_k, ld_v, ld_o, scale, k2, v2, n_kv2, ld_k2, ld_v2,
                               emu, st);
   const bool bn48 = split == 3 && P.d_pad <= 48;

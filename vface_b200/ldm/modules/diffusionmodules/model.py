@@ -119,10 +119,14 @@ class AttnBlock(nn.Module):
         t = _gn_silu(self.norm, xt, silu=False).reshape(n, hh * ww, c)
         lin = lambda conv: F.linear(t, conv.weight.reshape(c, c), conv.bias)
         q, k, v = lin(self.q), lin(self.k), lin(self.v)
-        if c <= 192 and c % 8 == 0 and x.dtype == torch.bfloat16:
-            o = ops.attention(q, k, v, heads=1, scale=float(c) ** -0.5)
-        else:
+        # one head of width c on the repo's own attention kernel: the tcgen05 path takes c <= 192 and the wide-head form
+        # 256 / 384 / 512 (REFace ddconfig: 512; csrc/vf_attn_stream.cu), the fp32 kernel c <= 256; anything else has no
+        # kernel here and fails loudly inside ops.attention
+        if x.dtype == torch.float32 and c > 256:
+            # reference-precision (fp32) decode of a 512-wide head: scores in fp32 through torch (parity path only)
             o = F.scaled_dot_product_attention(q.unsqueeze(1), k.unsqueeze(1), v.unsqueeze(1), scale=float(c) ** -0.5).squeeze(1)
+        else:
+            o = ops.attention(q.contiguous(), k.contiguous(), v.contiguous(), heads=1, scale=float(c) ** -0.5)
         o = F.linear(o, self.proj_out.weight.reshape(c, c))
         return ops.add_bias(xt, o.reshape(n, hh, ww, c), self.proj_out.bias).permute(0, 3, 1, 2)
 
