@@ -300,14 +300,15 @@ def shard_vs_single(sampler, rank, world, device, frames_per_rank, ddim_steps, s
 
 def verify_shard(rank, world, device):
     """--verify-shard: the strict form of D1 in the fp32 reference-precision path (and bf16 beside it): a 2-frames-per-rank
-    clip, 3 DDIM steps with hooks and flow, sharded over the ranks vs whole on one GPU; fp32 must agree to <= 1e-5."""
+    clip, 4 DDIM steps (3 is not a valid DDIM-step count for the reference's schedule) with hooks and flow,
+    sharded over the ranks vs whole on one GPU; fp32 must agree to <= 1e-5."""
     from vface_b200.ldm.models.diffusion.ddim_w_inv import DDIMSampler
     res = {}
     ok = True
     for name, dt in (("fp32", torch.float32), ("bf16", torch.bfloat16)):
         model, _ = build_model(device, dt)
         sampler = DDIMSampler(model)
-        r = shard_vs_single(sampler, rank, world, device, frames_per_rank=2, ddim_steps=3)
+        r = shard_vs_single(sampler, rank, world, device, frames_per_rank=2, ddim_steps=4)
         res[name] = r
         if name == "fp32":
             ok = ok and r["rel_l2_sharded_vs_single"] <= 1e-5
@@ -524,11 +525,18 @@ def main():
             torch.cuda.empty_cache()
             run.activate()
 
-    # ---- sharded == unsharded on real ranks, bf16, a small clip; --verify-shard is the strict
-    # fp32 form ------------------------------------------------------------------------------------------------------------
+    # ---- sharded == unsharded on real ranks: one small clip through DDIMSampler.sample, sharded
+    # over the ranks (halo over NCCL) vs whole on every rank.  fp32 reference-precision path (a second, fp32 copy of the
+    # UNet for the duration of the check): the two evaluations are the same computation up to the batch-size-dependent
+    # kernel choices of cuDNN / cuBLAS, i.e. fp32 round-off; in bf16 they would be two independent roundings ~1e-2 apart,
+    # which proves nothing.  --verify-shard runs a longer form and asserts. -----------------------------------------------
     shard_check = None
     if world > 1:
-        shard_check = shard_vs_single(sampler, rank, world, device, frames_per_rank=2, ddim_steps=2)
+        m32, _ = build_model(device, torch.float32, state=sd)
+        shard_check = shard_vs_single(DDIMSampler(m32), rank, world, device, frames_per_rank=2, ddim_steps=2)
+        shard_check["passed"] = bool(shard_check["rel_l2_sharded_vs_single"] <= 1e-5)
+        del m32
+        torch.cuda.empty_cache()
         run.activate()
 
     # ---- roofline of the dominant kernel (fused attention, N=4096) -------------------------------------

@@ -49,7 +49,8 @@ const char* vf_last_error(void);
  * Optional second key/value segment (k2, v2, n_kv2 rows) is treated as concatenated
  * after (k, v) along the key axis ("injected target-frame K/V"; BASELINE.json config 3;
  * no reference function).  Pass k2 = v2 = NULL, n_kv2 = 0 to disable.
- * d_head must be a multiple of 8, 8 <= d_head <= 192 (bf16) / <= 256 (fp32).
+ * d_head must be a multiple of 8: 8 <= d_head <= 192, or one of 256 / 384 / 512 (wide heads: the first-stage AttnBlock,
+ * ldm/modules/diffusionmodules/model.py:150-203, is one head of width 512) in bf16; <= 256 in fp32.
  */
 int vf_attn_fwd(const void* q, const void* k, const void* v, void* o,
                 int batch, int heads, int n_q, int n_kv, int d_head,
