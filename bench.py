@@ -337,6 +337,7 @@ def main():
                          "overrides --frames")
     ap.add_argument("--no-clip256", action="store_true", help="skip the secondary 256-frame strong-scaling measurement")
     ap.add_argument("--no-secondary", action="store_true", help="skip the per-kernel roofline_secondary pass")
+    ap.add_argument("--no-graph-extra", action="store_true", help="skip the secondary CUDA-graph-replay measurement (N=1 only)")
     ap.add_argument("--verify-shard", action="store_true",
                     help="correctness only (SURVEY.md section 4, D1): one clip sharded over the ranks == the same clip on one rank")
     args = ap.parse_args()
@@ -488,6 +489,39 @@ def main():
         elide_ms = t_e / ke
         sampler.elide_dead_recon = False
         run.activate()
+    # secondary figure: the same steps replayed as CUDA graphs (one graph per schedule position, captured on
+    # first use by DDIMSampler(cuda_graphs=True)).  Five schedule positions are captured, then replayed and timed.
+    graph_ms = None
+    if world == 1 and not args.no_graph_extra:
+        try:
+            kg = 5
+            common = dict(use_original_steps=False, quantize_denoised=False, temperature=1., noise_dropout=0., score_corrector=None,
+                          corrector_kwargs=None, unconditional_guidance_scale=CFG_SCALE, unconditional_conditioning=run.dev["uc"], **run.kw)
+
+            def graph_steps(xg):
+                for i in range(kg):
+                    xg, _ = sampler._graphed_step(xg, run.dev["c"], int(time_range[i]), DDIM_STEPS - 1 - i, run.dev["target_cond"],
+                                                  run.dev_flow, common)
+                return xg
+            with torch.no_grad():
+                xg = graph_steps(run.dev["x_T"])             # capture (with an eager warm-up each)
+                barrier()
+                g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                g0.record()
+                xg = graph_steps(run.dev["x_T"])             # replay
+                g1.record()
+                barrier()
+                xe = run.dev["x_T"]
+                for i in range(kg):
+                    xe = one_step(i, xe)
+                barrier()
+            graph_ms = dict(ms_per_step=g0.elapsed_time(g1) / kg, steps=kg, value=total_frames / (DDIM_STEPS * g0.elapsed_time(g1) / kg * 1e-3),
+                            unit=UNIT, identical_to_eager=bool(torch.equal(xg, xe)),
+                            note="the first 5 schedule positions replayed as CUDA graphs (DDIMSampler(cuda_graphs=True)); secondary figure")
+            sampler._graphs.clear()
+            torch.cuda.empty_cache()
+        except Exception as e:            # a secondary figure must never take the bench line down
+            graph_ms = dict(error=repr(e)[:300])
     lsum = torch.tensor([float(launches)], device=device, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(lsum, op=dist.ReduceOp.SUM)
@@ -619,7 +653,7 @@ def main():
                     higher_is_better=True, scaling="strong" if strong else "weak", vs_baseline=None, dtype="bf16",
                     data="synthetic", config=workload_config(frames, world, n_branches, strong),
                     clocks=clock_info, e2e=e2e, gpu_launches=int(lsum.item()), roofline=roof,
-                    roofline_secondary=secondary, cpu_baseline=cpu, elide_dead_recon=elide, clip256=clip256,
+                    roofline_secondary=secondary, cpu_baseline=cpu, elide_dead_recon=elide, clip256=clip256, cuda_graph=graph_ms,
                     shard_check=shard_check,
                     halo=dict(messages=shard.halo_messages, bytes=shard.halo_bytes) if world > 1 else None)
         print(json.dumps(line), flush=True)

@@ -405,3 +405,23 @@ def test_config0_eight_frames_vs_reference_golden(dtype, tol):
         want = gold[f"x_inter_w{wi}"]
         errs = [rel_l2(inter["x_inter"][1 + s], want[j]) for j, s in enumerate(kept)]
         assert max(errs) < tol, (wi, errs)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_cuda_graph_steps_match_eager(dtype):
+    """Extension: DDIMSampler(cuda_graphs=True) captures one CUDA graph per schedule position on the first
+    sample() call and replays them on the next; both calls, on two different clips, reproduce the eager sampler bit for bit
+    (same kernels, same order)."""
+    from oracle import kernels as ok
+    from vface_b200 import synth
+    S, B = 10, 2
+    steps = ok.make_schedule(S)["ddim_timesteps"]
+    _, eager, _ = build(SMALL, dtype)
+    _, graphed, _ = build(SMALL, dtype, cuda_graphs=True)
+    for seed in (7, 31):
+        clip = synth.synth_clip(B, seed=seed, steps=steps)
+        a, ia = run_sample(eager, clip, S, B, clip["inversion"])
+        b, ib = run_sample(graphed, clip, S, B, clip["inversion"])
+        assert torch.equal(a, b), seed
+        assert all(torch.equal(x, y) for x, y in zip(ia["x_inter"], ib["x_inter"]))
+    assert len(graphed._graphs) == S            # captured once, replayed for the second clip

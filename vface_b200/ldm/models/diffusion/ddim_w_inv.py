@@ -37,7 +37,7 @@ def load_ddim_latents_at_t(t, ddim_latents_path):
 
 
 class DDIMSampler(object):
-    def __init__(self, model, schedule="linear", elide_dead_recon=False, **kwargs):
+    def __init__(self, model, schedule="linear", elide_dead_recon=False, cuda_graphs=None, **kwargs):
         super().__init__()
         self.model = model
         self.ddpm_num_timesteps = model.num_timesteps
@@ -45,6 +45,13 @@ class DDIMSampler(object):
         self.elide_dead_recon = bool(elide_dead_recon)
         self.last_inversion = None          # {timestep: latents} of the most recent ddim_invert
         self._inv_cache = None
+        # Extension: one CUDA graph per denoising step, captured the first time a step of a given
+        # (schedule position, shapes) is run and replayed for every later batch of the clip -- the ~370 launches of a step
+        # become one.  Off by default (VF_CUDA_GRAPH=1 or cuda_graphs=True); single-rank only.
+        self.cuda_graphs = bool(int(os.environ.get("VF_CUDA_GRAPH", "0"))) if cuda_graphs is None else bool(cuda_graphs)
+        self._graphs = {}
+        self._graph_pool = None
+        self._graph_flow = None
 
     # -- buffers / schedule ----------------------------------------------------------------------
     def register_buffer(self, name, attr):
@@ -147,6 +154,18 @@ class DDIMSampler(object):
         time_range = np.flip(timesteps)
         total_steps = timesteps.shape[0]
 
+        graphs = (self.cuda_graphs and target_conditioning is not None and torch.device(device).type == "cuda"
+                  and not (frame_shard.current() is not None and frame_shard.current().world_size > 1)
+                  and mask is None and not callback and not img_callback
+                  and unconditional_conditioning is not None and unconditional_guidance_scale != 1.)
+        if graphs and flow is not None:
+            # the hooks keep the flow object they were registered with: give them a buffer whose address outlives the call
+            fl = ops._as_flow(flow, device)
+            if self._graph_flow is None or self._graph_flow.shape != fl.shape:
+                self._graph_flow = torch.empty_like(fl)
+                self._graphs.clear()
+            self._graph_flow.copy_(fl)
+            flow = self._graph_flow
         self._register_hooks(flow)
         self._inv_cache = None
         if target_conditioning is not None:
@@ -164,7 +183,9 @@ class DDIMSampler(object):
                           corrector_kwargs=corrector_kwargs,
                           unconditional_guidance_scale=unconditional_guidance_scale,
                           unconditional_conditioning=unconditional_conditioning, **kwargs)
-            if target_conditioning is not None:
+            if graphs:
+                outs = self._graphed_step(img, cond, int(step), index, target_conditioning, flow, common)
+            elif target_conditioning is not None:
                 outs = self.p_sample_ddim_with_inverse(img, cond, ts, target_conditioning=target_conditioning,
                                                        inverse_results_dir=inverse_results_dir, src_start=None,
                                                        flow=flow, _step=int(step), **common)
@@ -180,6 +201,58 @@ class DDIMSampler(object):
                 intermediates['pred_x0'].append(pred_x0)
         self._inv_cache = None
         return img, intermediates
+
+    # -- one reverse step as a CUDA graph (extension) ------------------------------------------------
+    def _graphed_step(self, img, cond, step, index, target_conditioning, flow, common):
+        """p_sample_ddim_with_inverse for schedule position `index` through a CUDA graph: captured on first use (after one
+        eager warm-up run on a side stream, which also creates the library plans and function attributes), replayed
+        afterwards with the inputs copied into the graph's static buffers.  The host-side scalars of the update
+        (a_t, a_prev, sigma_t, sqrt(1-a_t), the guidance scale) are kernel arguments, so they are part of the key."""
+        tmk = common.get("test_model_kwargs")
+        if tmk is None:
+            raise NotImplementedError("cuda_graphs needs test_model_kwargs (the VFace scripts' calling convention)")
+        uc = common["unconditional_conditioning"]
+        inv = self._inv_cache[step]
+        live = dict(img=img, cond=cond, tc=target_conditioning, uc=uc, ii=tmk["inpaint_image"], im=tmk["inpaint_mask"], inv=inv)
+        tb = self._host_tables
+        key = (index, step, float(tb["a_t"][index]), float(tb["a_prev"][index]), float(tb["sigma"][index]),
+               float(common["unconditional_guidance_scale"]), float(common.get("temperature", 1.)), self.elide_dead_recon,
+               tuple((k, tuple(v.shape), v.dtype) for k, v in live.items()), None if flow is None else flow.data_ptr(),
+               next(self.model.model.diffusion_model.parameters()).dtype)
+        entry = self._graphs.get(key)
+        if entry is None:
+            static = {k: v.clone() for k, v in live.items()}
+
+            def run():
+                kw = dict(common)
+                kw["test_model_kwargs"] = dict(inpaint_image=static["ii"], inpaint_mask=static["im"])
+                kw["unconditional_conditioning"] = static["uc"]
+                saved = self._inv_cache
+                self._inv_cache = {step: static["inv"]}
+                try:
+                    ts = torch.full((static["img"].shape[0],), step, device=static["img"].device, dtype=torch.long)
+                    return self.p_sample_ddim_with_inverse(static["img"], static["cond"], ts, target_conditioning=static["tc"],
+                                                           inverse_results_dir=None, src_start=None, flow=flow, _step=step, **kw)
+                finally:
+                    self._inv_cache = saved
+
+            cur = torch.cuda.current_stream()
+            side = torch.cuda.Stream()
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                run()                                   # warm-up: library plans, function attributes, allocator
+            cur.wait_stream(side)
+            g = torch.cuda.CUDAGraph()
+            if self._graph_pool is None:
+                self._graph_pool = torch.cuda.graph_pool_handle()
+            with torch.cuda.graph(g, pool=self._graph_pool):
+                out = run()
+            entry = self._graphs[key] = (g, static, out)
+        g, static, out = entry
+        for k, v in live.items():
+            static[k].copy_(v)
+        g.replay()
+        return out[0].clone(), out[1].clone()
 
     # -- one reverse step --------------------------------------------------------------------------
     @staticmethod
