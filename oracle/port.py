@@ -208,8 +208,8 @@ def vface_hooks(sd: SD, flow, fusion="flow_fix", split_ratio_fft=0.8, alpha=0.8,
 def sample(sd: SD, heads: int, S: int, x_T, cond, target_cond, uc, inpaint_image, inpaint_mask, inversion: dict,
            flow, scale: float = 3.0, eta: float = 0.0, hooks_fusion="flow_fix", return_all=False, max_steps=None,
            step_callback=None):
-    """DDIMSampler.sample -> ddim_sampling -> p_sample_ddim_with_inverse (eta = 0 path: the two noise
-    draws of the reference are multiplied by sigma = 0 and do not affect the result)."""
+    """DDIMSampler.sample -> ddim_sampling -> p_sample_ddim_with_inverse (ddim_w_inv.py:186-355, :621-738); noise comes
+    from the global CPU generator exactly as in the reference (two draws per step)."""
     tb = ok.make_schedule(S, eta)
     steps = tb["ddim_timesteps"]
     hooks = vface_hooks(sd, flow, fusion=hooks_fusion) if hooks_fusion else {}
@@ -227,9 +227,12 @@ def sample(sd: SD, heads: int, S: int, x_T, cond, target_cond, uc, inpaint_image
         x_in = torch.cat([x_full, x_full, inv_full], dim=0)
         c_in = torch.cat([uc, cond, target_cond], dim=0).float()
         e_u, e_c, _ = unet_forward(sd, x_in, torch.cat([ts] * 3), c_in, heads, hooks).chunk(3)
-        noise = None
-        if eta > 0:
-            noise = torch.randn(img.shape).numpy()
+        # noise_like is called TWICE per step, whatever eta is (ddim_w_inv.py:697 for x_prev, :704 for the discarded recon
+        # branch): the first draw is the noise of x_prev, the second only advances the generator
+        noise = torch.randn(img.shape).numpy()
+        torch.randn(img.shape)
+        if eta == 0:
+            noise = None
         x_prev, pred_x0 = ok.ddim_cfg_step(img.numpy(), e_u.numpy(), e_c.numpy(), tb["ddim_alphas"][index],
                                            tb["ddim_alphas_prev"][index], tb["ddim_sigmas"][index],
                                            tb["ddim_sqrt_one_minus_alphas"][index], scale, noise)
@@ -239,3 +242,24 @@ def sample(sd: SD, heads: int, S: int, x_T, cond, target_cond, uc, inpaint_image
         if step_callback:
             step_callback(i, img)
     return (img, xs, x0s) if return_all else img
+
+
+@torch.no_grad()
+def p_sample_ddim(sd: SD, heads: int, S: int, index: int, step: int, x, cond, uc, inpaint_image, inpaint_mask,
+                  scale: float = 3.0, eta: float = 0.0):
+    """DDIMSampler.p_sample_ddim (ddim_w_inv.py:564-617): the 2-way [uncond ; cond] step on an un-hooked UNet (one branch
+    when scale == 1, :577-578); ONE noise draw (:611)."""
+    tb = ok.make_schedule(S, eta)
+    b = x.shape[0]
+    ts = torch.full((b,), int(step), dtype=torch.long)
+    x_full = torch.cat([x.float(), inpaint_image.float(), inpaint_mask.float()], dim=1)
+    if uc is None or scale == 1.0:
+        e_c = unet_forward(sd, x_full, ts, cond.float(), heads, {})
+        e_u, scale = e_c, 1.0
+    else:
+        e_u, e_c = unet_forward(sd, torch.cat([x_full] * 2), torch.cat([ts] * 2), torch.cat([uc, cond]).float(), heads, {}).chunk(2)
+    noise = torch.randn(x.shape).numpy()
+    x_prev, pred_x0 = ok.ddim_cfg_step(x.float().numpy(), e_u.numpy(), e_c.numpy(), tb["ddim_alphas"][index], tb["ddim_alphas_prev"][index],
+                                       tb["ddim_sigmas"][index], tb["ddim_sqrt_one_minus_alphas"][index], scale,
+                                       noise if eta > 0 else None)
+    return torch.from_numpy(x_prev), torch.from_numpy(pred_x0)

@@ -225,6 +225,8 @@ class DDIMSampler(object):
 
             def run():
                 kw = dict(common)
+                kw.pop("index", None)
+                kw["index"] = index
                 kw["test_model_kwargs"] = dict(inpaint_image=static["ii"], inpaint_mask=static["im"])
                 kw["unconditional_conditioning"] = static["uc"]
                 saved = self._inv_cache

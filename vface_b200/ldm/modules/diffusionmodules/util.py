@@ -57,12 +57,20 @@ def make_ddim_sampling_parameters(alphacums, ddim_timesteps, eta, verbose=True):
     return sigmas, alphas, alphas_prev
 
 
+_FREQS = {}
+
+
 def timestep_embedding(timesteps, dim, max_period=10000, repeat_only=False):
     """Sinusoidal embedding [cos | sin] of (N,) timesteps -> (N, dim) fp32 (reference util.py:151-171)."""
     if repeat_only:
         return timesteps[:, None].expand(-1, dim)
     half = dim // 2
-    freqs = torch.exp(-math.log(max_period) * torch.arange(half, dtype=torch.float32) / half).to(timesteps.device)
+    # computed on the host like the reference (bit-identical frequencies), but only once per (half, period, device): the
+    # per-call host -> device copy of the reference is also what makes a step impossible to capture in a CUDA graph
+    key = (half, max_period, timesteps.device)
+    freqs = _FREQS.get(key)
+    if freqs is None:
+        freqs = _FREQS[key] = torch.exp(-math.log(max_period) * torch.arange(half, dtype=torch.float32) / half).to(timesteps.device)
     args = timesteps[:, None].float() * freqs[None]
     emb = torch.cat([torch.cos(args), torch.sin(args)], dim=-1)
     if dim % 2:
