@@ -304,6 +304,265 @@ static void gn_plan(int n, int hw, int* slabs, int* rows_per_slab) {
   *slabs = (hw + rps - 1) / rps;
 }
 
+// ---- fused GroupNorm: ONE persistent launch, the apply pass re-reads its slab out of L2 ----------------------
+// The two launches above stream x from HBM twice (the tensor of a 96-sample step does not fit the 126 MB L2 between
+// them) and pay two grid tails.  Here a persistent grid takes (sample, slab) work items off a ticket counter in
+// sample-major order; a CTA reduces the statistics of its slab, publishes them, waits until every slab of ITS
+// sample has arrived (a per-sample counter: the other slabs are held by CTAs that took their tickets at about the
+// same time), and applies the normalisation to the SAME slab right away -- the second read of x hits L2 as long as
+// (resident CTAs x slab bytes) stays well below the L2 size, which the slab plan below guarantees (~36 MB).
+//   * tickets make the wait deadlock-free without assuming a block dispatch order: every lower ticket is held by a
+//     CTA that is already running (it only waits on tickets lower than or next to its own);
+//   * statistics stay bit-reproducible: per-slab partials in a fixed order, per-sample totals in a fixed order;
+//   * the counters clean up after themselves (the last CTA to leave a sample / the grid resets them), live in
+//     module-global memory and are rotated over kGnSyncSets launches.
+//   * the block is tpr x rpb threads (chunks per row x rows per trip, rounded up to a warp) so no lane idles at
+//     c = 1280 / 1920 / 2560, and every thread keeps kGnfUnroll 16-byte loads in flight.
+constexpr int kGnfMaxThreads = 320;
+constexpr int kGnSyncSets = 4;
+constexpr int kGnfMaxN = 4096;
+__device__ unsigned int g_gn_sync[kGnSyncSets][2 + 2 * kGnfMaxN];     // ticket, finished, then (arrived, departed) per sample
+
+__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+template <typename T, int U, int kMinB>     // U 16-byte loads in flight per thread, kMinB CTAs per SM
+__global__ void __launch_bounds__(kGnfMaxThreads, kMinB)
+gn_fused_kernel(const GnParams P, const int tpr, const int rpb, const int set) {
+  constexpr int E = V16<T>::E;
+  extern __shared__ float s_part[];                     // [2][rpb * c] per-(row lane, channel) partials
+  __shared__ float s_mean[kGnMaxGroups], s_rstd[kGnMaxGroups];
+  __shared__ double s_red[kGnfMaxThreads / 32][kGnMaxGroups][2];
+  __shared__ int s_item;
+  unsigned int* sync = g_gn_sync[set];
+  const int tid = threadIdx.x;
+  const int my_row = tid / tpr, my_chunk = tid - my_row * tpr;
+  const bool active = my_row < rpb;
+  const int ch = my_chunk * E;
+  const int cpg = P.c / P.groups;
+  const int c2 = P.c - P.c1;
+  const int total = P.n * P.slabs;
+  float* s_psum = s_part;
+  float* s_psq = s_part + rpb * P.c;
+  const bool from1 = ch < P.c1;
+  const int ld = from1 ? P.c1 : c2;                     // row stride of the source this thread reads
+  const int ch_src = from1 ? ch : ch - P.c1;
+
+  for (;;) {
+    if (tid == 0) s_item = (int)atomicAdd(&sync[0], 1u);
+    __syncthreads();
+    const int item = s_item;
+    if (item >= total) break;
+    const int n = item / P.slabs, slab = item - n * P.slabs;
+    const int r0 = slab * P.rows_per_slab;
+    const int r1 = min(P.hw, r0 + P.rows_per_slab);
+    const T* src = (from1 ? reinterpret_cast<const T*>(P.x) : reinterpret_cast<const T*>(P.x2)) + (size_t)n * P.hw * ld + ch_src;
+    T* dst = reinterpret_cast<T*>(P.y) + (size_t)n * P.hw * P.c + ch;
+    // ---- phase 1: statistics of the slab ---------------------------------------------------------------
+    // The additive vector a[c] stays out of the loop (and out of the registers the loads in flight need):
+    // sum(x + a) = sum(x) + N a,  sum((x + a)^2) = sum(x^2) + a (2 sum(x) + N a).
+    if (active) {
+      float sum[E], sq[E];
+#pragma unroll
+      for (int j = 0; j < E; ++j) { sum[j] = 0.f; sq[j] = 0.f; }
+      int r = r0 + my_row;
+      const int my_rows = r < r1 ? (r1 - r + rpb - 1) / rpb : 0;
+      // one running pointer, all U loads issued before the first use (address arithmetic per load would eat the
+      // registers the loads in flight need and ptxas then interleaves use and issue: two loads in flight, not U)
+      const char* p = reinterpret_cast<const char*>(src) + (size_t)r * ld * sizeof(T);
+      const size_t stride = (size_t)rpb * ld * sizeof(T);
+      for (; r + (U - 1) * rpb < r1; r += U * rpb) {
+        uint4 raw[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) { raw[u] = ld_nc_v4(p); p += stride; }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          float v[E];
+          V16<T>::unpack(raw[u], v);
+#pragma unroll
+          for (int j = 0; j < E; ++j) { sum[j] += v[j]; sq[j] = fmaf(v[j], v[j], sq[j]); }
+        }
+      }
+      for (; r < r1; r += rpb, p += stride) {             // ragged tail (the slab plan makes it rare)
+        float v[E];
+        V16<T>::unpack(ld_nc_v4(p), v);
+#pragma unroll
+        for (int j = 0; j < E; ++j) { sum[j] += v[j]; sq[j] = fmaf(v[j], v[j], sq[j]); }
+      }
+      if (P.add_nc) {
+        float av[E];
+        V16<T>::ld(reinterpret_cast<const T*>(P.add_nc) + (size_t)n * P.c + ch, av);
+        const float cnt = (float)my_rows;
+#pragma unroll
+        for (int j = 0; j < E; ++j) {
+          sq[j] = fmaf(av[j], fmaf(cnt, av[j], 2.0f * sum[j]), sq[j]);
+          sum[j] = fmaf(cnt, av[j], sum[j]);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < E; ++j) {
+        s_psum[my_row * P.c + ch + j] = sum[j];
+        s_psq[my_row * P.c + ch + j] = sq[j];
+      }
+    }
+    __syncthreads();
+    // eight lanes per group, channels strided over the lanes, row lanes in order, then a fixed shuffle tree
+    for (int grp = tid >> 3; grp < P.groups; grp += blockDim.x >> 3) {       // blockDim is a multiple of 32
+      const int sub = tid & 7;
+      float gs = 0.f, gq = 0.f;
+      for (int i = sub; i < cpg; i += 8)
+        for (int rr = 0; rr < rpb; ++rr) {
+          gs += s_psum[rr * P.c + grp * cpg + i];
+          gq += s_psq[rr * P.c + grp * cpg + i];
+        }
+      const unsigned m8 = 0xffu << (tid & 24);           // the eight lanes of this group (they share grp)
+#pragma unroll
+      for (int o = 4; o > 0; o >>= 1) {
+        gs += __shfl_xor_sync(m8, gs, o);
+        gq += __shfl_xor_sync(m8, gq, o);
+      }
+      if (sub == 0) {
+        float* w = P.ws + (((size_t)n * P.slabs + slab) * P.groups + grp) * 2;
+        __stcg(w, gs);
+        __stcg(w + 1, gq);
+      }
+    }
+    __syncthreads();
+    if (tid == 0) {
+      __threadfence();                                   // the CTA's partials (ordered by the barrier) before the arrival
+      atomicAdd(&sync[2 + 2 * n], 1u);
+      while (ld_acquire_u32(&sync[2 + 2 * n]) < (unsigned)P.slabs) __nanosleep(64);
+      // everyone who departs has passed the wait: the last one may clear the sample's counters for the next launch
+      const unsigned d = atomicAdd(&sync[3 + 2 * n], 1u);
+      if (d == (unsigned)P.slabs - 1u) { sync[2 + 2 * n] = 0u; sync[3 + 2 * n] = 0u; }
+    }
+    __syncthreads();
+
+    // ---- totals of the sample (fixed order), mean / rstd per group -------------------------------------
+    {
+      const int grp = tid & 31, part = tid >> 5, parts = blockDim.x >> 5;
+      if (grp < P.groups) {
+        double s = 0.0, q = 0.0;
+        for (int i = part; i < P.slabs; i += parts) {
+          const float* w = P.ws + (((size_t)n * P.slabs + i) * P.groups + grp) * 2;
+          s += (double)__ldcg(w);
+          q += (double)__ldcg(w + 1);
+        }
+        s_red[part][grp][0] = s;
+        s_red[part][grp][1] = q;
+      }
+      __syncthreads();
+      if (tid < P.groups) {
+        double s = 0.0, q = 0.0;
+        for (int p = 0; p < parts; ++p) { s += s_red[p][tid][0]; q += s_red[p][tid][1]; }
+        const double cnt = (double)P.hw * cpg;
+        const double mean = s / cnt;
+        double var = q / cnt - mean * mean;
+        if (var < 0.0) var = 0.0;
+        s_mean[tid] = (float)mean;
+        s_rstd[tid] = (float)(1.0 / sqrt(var + (double)P.eps));
+      }
+      __syncthreads();
+    }
+
+    // ---- phase 2: apply to the same slab (x comes back out of L2) ------------------------------------------
+    if (active) {
+      float scale[E], shift[E], gam[E], bet[E];          // gamma / beta re-read per item (L1/L2 hits): 16 registers
+      V16<T>::ld(reinterpret_cast<const T*>(P.gamma) + ch, gam);      // that phase 1 needs for loads in flight
+      V16<T>::ld(reinterpret_cast<const T*>(P.beta) + ch, bet);
+      float av[E];
+#pragma unroll
+      for (int j = 0; j < E; ++j) av[j] = 0.f;
+      if (P.add_nc) V16<T>::ld(reinterpret_cast<const T*>(P.add_nc) + (size_t)n * P.c + ch, av);
+#pragma unroll
+      for (int j = 0; j < E; ++j) {
+        const int grp = (ch + j) / cpg;
+        scale[j] = s_rstd[grp] * gam[j];
+        shift[j] = fmaf(av[j] - s_mean[grp], scale[j], bet[j]);        // (x + a - mean) * rstd * gamma + beta
+      }
+      int r = r0 + my_row;
+      const char* p = reinterpret_cast<const char*>(src) + (size_t)r * ld * sizeof(T);
+      char* q = reinterpret_cast<char*>(dst) + (size_t)r * P.c * sizeof(T);
+      const size_t stride = (size_t)rpb * ld * sizeof(T);
+      const size_t qstride = (size_t)rpb * P.c * sizeof(T);
+      for (; r + (U - 1) * rpb < r1; r += U * rpb) {
+        uint4 raw[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) { raw[u] = ld_nc_v4(p); p += stride; }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          float v[E];
+          V16<T>::unpack(raw[u], v);
+#pragma unroll
+          for (int j = 0; j < E; ++j) {
+            float t = fmaf(v[j], scale[j], shift[j]);
+            if (P.silu) t = silu_f<T>(t);
+            v[j] = t;
+          }
+          st_na_v4(q, V16<T>::pack(v));
+          q += qstride;
+        }
+      }
+      for (; r < r1; r += rpb, p += stride, q += qstride) {
+        float v[E];
+        V16<T>::unpack(ld_nc_v4(p), v);
+#pragma unroll
+        for (int j = 0; j < E; ++j) {
+          float t = fmaf(v[j], scale[j], shift[j]);
+          if (P.silu) t = silu_f<T>(t);
+          v[j] = t;
+        }
+        st_na_v4(q, V16<T>::pack(v));
+      }
+    }
+  }
+  // the last CTA out re-arms the ticket counter (nobody takes a ticket after leaving the loop)
+  if (tid == 0) {
+    __threadfence();
+    const unsigned f = atomicAdd(&sync[1], 1u);
+    if (f == gridDim.x - 1u) { sync[0] = 0u; sync[1] = 0u; }
+  }
+}
+
+// VF_GN_FUSED_CTAS: 2 (default) = two CTAs per SM with eight loads in flight per thread (96 registers);
+// 3 = three CTAs per SM with four (64 registers: eight spill).
+static int gnf_ctas_per_sm() {
+  static int v = -1;
+  if (v < 0) { const char* e_ = getenv("VF_GN_FUSED_CTAS"); v = e_ ? atoi(e_) : 2; if (v != 3) v = 2; }
+  return v;
+}
+
+// Slab plan of the fused kernel: slabs of ~slab_kb KB, a whole number of unrolled trips, at most 64 per sample.
+static void gnf_plan(int hw, int c, int esize, int rpb, int slab_kb, int* slabs, int* rows_per_slab) {
+  const int trip = (gnf_ctas_per_sm() == 3 ? 4 : 8) * rpb;
+  const long long row_bytes = (long long)c * esize;
+  long long rows = ((long long)slab_kb * 1024 + row_bytes - 1) / row_bytes;
+  rows = (rows + trip - 1) / trip * trip;
+  if (rows > hw) rows = hw;
+  if (rows < 1) rows = 1;
+  int s = (int)((hw + rows - 1) / rows);
+  while (s > 64) { rows += trip; s = (int)((hw + rows - 1) / rows); }
+  *slabs = s;
+  *rows_per_slab = (int)rows;
+}
+
+template <typename T>
+static int gn_fused_launch(GnParams& P, int tpr, int rpb, int threads, cudaStream_t st) {
+  const int ctas_per_sm = gnf_ctas_per_sm();
+  static unsigned launch_no = 0;
+  const int set = (int)(launch_no++ % kGnSyncSets);
+  const size_t smem = (size_t)2 * rpb * P.c * sizeof(float);
+  long long grid = (long long)P.n * P.slabs;
+  const long long cap = (long long)ctas_per_sm * num_sms();
+  if (grid > cap) grid = cap;
+  if (ctas_per_sm == 3) gn_fused_kernel<T, 4, 3><<<(int)grid, threads, smem, st>>>(P, tpr, rpb, set);
+  else gn_fused_kernel<T, 8, 2><<<(int)grid, threads, smem, st>>>(P, tpr, rpb, set);
+  return check_cuda(cudaGetLastError(), "gn_fused_kernel launch");
+}
+
 // ---- one-pass GroupNorm: a thread-block cluster per sample, the sample resident in shared memory ------------
 // The two-pass form reads x twice (statistics, apply): 3 HBM passes.  Here a cluster of 1..16 CTAs owns one
 // sample: each CTA pulls its contiguous slab of rows into shared memory with 1-D bulk TMA copies (chunked, so
@@ -527,6 +786,252 @@ static int gn_cluster_launch(GnParams& P, int cs, size_t smem, cudaStream_t st) 
     ok_smem[cs] = smem;
   }
   return check_cuda(cudaLaunchKernelEx(&cfg, gn_cluster_kernel<T, CPT>, P), "gn_cluster_kernel launch");
+}
+
+// ---- resident GroupNorm: the fused persistent kernel with the slab held in shared memory ----------------------
+// Same work items, tickets and per-sample counters as gn_fused_kernel, but a CTA pulls its slab (<= ~100 KB, a
+// contiguous run of rows per source) into shared memory with 1-D bulk copies (cp.async.bulk, kGnrChunks pieces on
+// their own mbarriers, so the statistics run under the loads and the whole slab is in flight at once, which no
+// register-staged loop can afford), and the apply pass reads shared memory: x crosses HBM ONCE, y once.  Two CTAs
+// per SM: while one streams its slab in, the other streams its result out.
+constexpr int kGnrChunks = 8;
+constexpr int kGnrMaxSlabs = 128;
+
+struct GnrHeader {
+  uint64_t bar[kGnrChunks];
+  float mean[kGnMaxGroups], rstd[kGnMaxGroups];
+  double red[kGnfMaxThreads / 32][kGnMaxGroups][2];
+  int item;
+};
+constexpr int kGnrHeaderBytes = 6 * 1024;
+static_assert(sizeof(GnrHeader) <= kGnrHeaderBytes, "header");
+
+template <typename T>
+__global__ void __launch_bounds__(kGnfMaxThreads, 2)
+gn_resident_kernel(const GnParams P, const int tpr, const int rpb, const int set) {
+  constexpr int E = V16<T>::E;
+  extern __shared__ __align__(128) unsigned char gnr_smem[];
+  GnrHeader* H = reinterpret_cast<GnrHeader*>(gnr_smem);
+  float4* s_pair = reinterpret_cast<float4*>(gnr_smem + kGnrHeaderBytes);          // per thread: (sum, sq) of its two groups
+  T* slab1 = reinterpret_cast<T*>(gnr_smem + kGnrHeaderBytes + kGnfMaxThreads * sizeof(float4));
+  unsigned int* sync = g_gn_sync[set];
+  const int tid = threadIdx.x;
+  const int my_row = tid / tpr, my_chunk = tid - my_row * tpr;
+  const bool active = my_row < rpb;
+  const int ch = my_chunk * E;
+  const int cpg = P.c / P.groups;                       // >= E: a 16-byte chunk touches at most two groups
+  const int c1 = P.c1, c2 = P.c - P.c1;
+  const int total = P.n * P.slabs;
+  T* slab2 = slab1 + (size_t)P.rows_per_slab * c1;
+  const bool from1 = ch < c1;
+  const int ld = from1 ? c1 : c2;
+  const T* my_slab = from1 ? slab1 + ch : slab2 + (ch - c1);
+  const int g_lo = ch / cpg;
+  const int n_lo = min(E, (g_lo + 1) * cpg - ch);       // channels of the chunk that belong to g_lo
+
+  if (tid == 0) {
+    for (int k = 0; k < kGnrChunks; ++k) sm100::mbar_init(&H->bar[k], 1);
+    sm100::fence_barrier_init();
+  }
+  uint32_t phase = 0;
+  for (;; phase ^= 1u) {
+    if (tid == 0) H->item = (int)atomicAdd(&sync[0], 1u);
+    __syncthreads();                                    // also: every thread is done with the previous slab
+    const int item = H->item;
+    if (item >= total) break;
+    const int n = item / P.slabs, slab = item - n * P.slabs;
+    const int r0 = slab * P.rows_per_slab;
+    const int nrows = min(P.hw, r0 + P.rows_per_slab) - r0;
+    int rows_per_chunk = (nrows + kGnrChunks - 1) / kGnrChunks;
+    rows_per_chunk = (rows_per_chunk + rpb - 1) / rpb * rpb;        // a thread's rows do not depend on the chunking
+    if (tid == 0) {
+      const T* g1 = reinterpret_cast<const T*>(P.x) + ((size_t)n * P.hw + r0) * c1;
+      const T* g2 = c2 ? reinterpret_cast<const T*>(P.x2) + ((size_t)n * P.hw + r0) * c2 : nullptr;
+      for (int k = 0; k < kGnrChunks; ++k) {
+        const int a = min(nrows, k * rows_per_chunk), b = min(nrows, (k + 1) * rows_per_chunk);
+        const uint32_t b1 = (uint32_t)((size_t)(b - a) * c1 * sizeof(T));
+        const uint32_t b2 = c2 ? (uint32_t)((size_t)(b - a) * c2 * sizeof(T)) : 0u;
+        sm100::mbar_arrive_expect_tx(&H->bar[k], b1 + b2);            // 0 bytes: completes at once
+        if (b1) bulk_g2s(slab1 + (size_t)a * c1, g1 + (size_t)a * c1, b1, &H->bar[k]);
+        if (b2) bulk_g2s(slab2 + (size_t)a * c2, g2 + (size_t)a * c2, b2, &H->bar[k]);
+      }
+    }
+
+    // parameters of phase 2 now: their latency hides under the slab load instead of sitting behind the sample wait
+    float gam[E], bet[E], av[E];
+#pragma unroll
+    for (int j = 0; j < E; ++j) { gam[j] = 0.f; bet[j] = 0.f; av[j] = 0.f; }
+    if (active) {
+      V16<T>::ld(reinterpret_cast<const T*>(P.gamma) + ch, gam);
+      V16<T>::ld(reinterpret_cast<const T*>(P.beta) + ch, bet);
+      if (P.add_nc) V16<T>::ld(reinterpret_cast<const T*>(P.add_nc) + (size_t)n * P.c + ch, av);
+    }
+
+    // ---- phase 1: statistics as the chunks land --------------------------------------------------------
+    {
+      float sum[E], sq[E];
+#pragma unroll
+      for (int j = 0; j < E; ++j) { sum[j] = 0.f; sq[j] = 0.f; }
+      int r = my_row;
+      for (int kc = 0; kc < kGnrChunks; ++kc) {
+        sm100::mbar_wait(&H->bar[kc], phase);
+        const int b = min(nrows, (kc + 1) * rows_per_chunk);
+        if (active) {
+          for (; r < b; r += rpb) {
+            float v[E];
+            V16<T>::ld(my_slab + (size_t)r * ld, v);
+#pragma unroll
+            for (int j = 0; j < E; ++j) { sum[j] += v[j]; sq[j] = fmaf(v[j], v[j], sq[j]); }
+          }
+        }
+      }
+      if (active) {
+        if (P.add_nc) {                                   // sum(x + a) = sum(x) + N a, sum((x + a)^2) = sum(x^2) + a (2 sum(x) + N a)
+          const float cnt = (float)(my_row < nrows ? (nrows - my_row + rpb - 1) / rpb : 0);
+#pragma unroll
+          for (int j = 0; j < E; ++j) {
+            sq[j] = fmaf(av[j], fmaf(cnt, av[j], 2.0f * sum[j]), sq[j]);
+            sum[j] = fmaf(cnt, av[j], sum[j]);
+          }
+        }
+        float4 pr = make_float4(0.f, 0.f, 0.f, 0.f);      // (sum, sq) of g_lo, (sum, sq) of g_lo + 1
+#pragma unroll
+        for (int j = 0; j < E; ++j) {
+          if (j < n_lo) { pr.x += sum[j]; pr.y += sq[j]; }
+          else { pr.z += sum[j]; pr.w += sq[j]; }
+        }
+        s_pair[tid] = pr;
+      }
+    }
+    __syncthreads();
+    // group totals of the slab: eight lanes per group over (row lane, chunk) in a fixed order, then a fixed tree
+    for (int grp = tid >> 3; grp < P.groups; grp += blockDim.x >> 3) {
+      const int sub = tid & 7;
+      const int k0 = (grp * cpg) / E, k1 = ((grp + 1) * cpg - 1) / E;       // chunks that touch the group
+      const int nk = k1 - k0 + 1;
+      float gs = 0.f, gq = 0.f;
+      for (int i = sub; i < nk * rpb; i += 8) {
+        const int rr = i / nk, k = k0 + (i - rr * nk);
+        const float4 pr = s_pair[rr * tpr + k];
+        const bool lo = (k * E) / cpg == grp;
+        gs += lo ? pr.x : pr.z;
+        gq += lo ? pr.y : pr.w;
+      }
+      const unsigned m8 = 0xffu << (tid & 24);
+#pragma unroll
+      for (int o = 4; o > 0; o >>= 1) {
+        gs += __shfl_xor_sync(m8, gs, o);
+        gq += __shfl_xor_sync(m8, gq, o);
+      }
+      if (sub == 0) {
+        float* w = P.ws + (((size_t)n * P.slabs + slab) * P.groups + grp) * 2;
+        __stcg(w, gs);
+        __stcg(w + 1, gq);
+      }
+    }
+    __syncthreads();
+    if (tid == 0) {
+      __threadfence();
+      atomicAdd(&sync[2 + 2 * n], 1u);
+      while (ld_acquire_u32(&sync[2 + 2 * n]) < (unsigned)P.slabs) __nanosleep(64);
+      const unsigned d = atomicAdd(&sync[3 + 2 * n], 1u);
+      if (d == (unsigned)P.slabs - 1u) { sync[2 + 2 * n] = 0u; sync[3 + 2 * n] = 0u; }
+    }
+    __syncthreads();
+    // totals of the sample: eight lanes per group, slabs strided over the lanes (their loads go out together: one L2
+    // round trip for up to 32 slabs), then a fixed shuffle tree in double -- the same order in every CTA of the sample
+    if (tid < 8 * P.groups) {
+      const int grp = tid >> 3, sub = tid & 7;
+      double sd = 0.0, qd = 0.0;
+      const float2* w = reinterpret_cast<const float2*>(P.ws) + ((size_t)n * P.slabs) * P.groups + grp;
+      for (int i0 = sub; i0 < P.slabs; i0 += 32) {
+        float2 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int i = i0 + 8 * u;
+          v[u] = i < P.slabs ? __ldcg(w + (size_t)i * P.groups) : make_float2(0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { sd += (double)v[u].x; qd += (double)v[u].y; }
+      }
+      const unsigned m8 = 0xffu << (tid & 24);
+#pragma unroll
+      for (int o = 4; o > 0; o >>= 1) {
+        sd += __shfl_xor_sync(m8, sd, o);
+        qd += __shfl_xor_sync(m8, qd, o);
+      }
+      if (sub == 0) {
+        const double cnt = (double)P.hw * cpg;
+        const double mean = sd / cnt;
+        double var = qd / cnt - mean * mean;
+        if (var < 0.0) var = 0.0;
+        H->mean[grp] = (float)mean;
+        H->rstd[grp] = (float)(1.0 / sqrt(var + (double)P.eps));
+      }
+    }
+    __syncthreads();
+
+    // ---- phase 2: apply out of shared memory --------------------------------------------------------------
+    if (active) {
+      float scale[E], shift[E];
+#pragma unroll
+      for (int j = 0; j < E; ++j) {
+        const int grp = (ch + j) / cpg;
+        scale[j] = H->rstd[grp] * gam[j];
+        shift[j] = fmaf(av[j] - H->mean[grp], scale[j], bet[j]);
+      }
+      char* q = reinterpret_cast<char*>(reinterpret_cast<T*>(P.y) + ((size_t)n * P.hw + r0 + my_row) * P.c + ch);
+      const size_t qstride = (size_t)rpb * P.c * sizeof(T);
+#pragma unroll 4
+      for (int r = my_row; r < nrows; r += rpb, q += qstride) {
+        float v[E];
+        V16<T>::ld(my_slab + (size_t)r * ld, v);
+#pragma unroll
+        for (int j = 0; j < E; ++j) {
+          float t = fmaf(v[j], scale[j], shift[j]);
+          if (P.silu) t = silu_f<T>(t);
+          v[j] = t;
+        }
+        st_na_v4(q, V16<T>::pack(v));
+      }
+    }
+  }
+  if (tid == 0) {
+    __threadfence();
+    const unsigned f = atomicAdd(&sync[1], 1u);
+    if (f == gridDim.x - 1u) { sync[0] = 0u; sync[1] = 0u; }
+  }
+}
+
+// slab plan: the largest slab (a multiple of rpb rows) within `budget` bytes; 0 slabs = does not fit the scheme
+static void gnr_plan(int hw, int c, int esize, int rpb, size_t budget, int* slabs, int* rows_per_slab) {
+  long long rows = (long long)(budget / ((size_t)c * esize));
+  rows = rows / rpb * rpb;
+  if (rows > hw) rows = (hw + rpb - 1) / rpb * rpb;
+  if (rows < rpb) { *slabs = 0; *rows_per_slab = 0; return; }
+  int s = (int)((hw + rows - 1) / rows);
+  // even the slabs out (the last one would otherwise be a sliver)
+  rows = ((hw + s - 1) / s + rpb - 1) / rpb * rpb;
+  s = (int)((hw + rows - 1) / rows);
+  *slabs = s > kGnrMaxSlabs ? 0 : s;
+  *rows_per_slab = (int)rows;
+}
+
+template <typename T>
+static int gn_resident_launch(GnParams& P, int tpr, int rpb, int threads, cudaStream_t st) {
+  static unsigned launch_no = 0;
+  const int set = (int)(launch_no++ % kGnSyncSets);
+  const size_t smem = kGnrHeaderBytes + kGnfMaxThreads * sizeof(float4) + (size_t)P.rows_per_slab * P.c * sizeof(T);
+  static size_t attr = 0;
+  if (smem > attr) {
+    VF_CUDA_TRY(cudaFuncSetAttribute(gn_resident_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+    attr = 112 * 1024;
+  }
+  long long grid = (long long)P.n * P.slabs;
+  const long long cap = 2LL * num_sms();
+  if (grid > cap) grid = cap;
+  gn_resident_kernel<T><<<(int)grid, threads, smem, st>>>(P, tpr, rpb, set);
+  return check_cuda(cudaGetLastError(), "gn_resident_kernel launch");
 }
 
 // ================================================================================================
@@ -898,7 +1403,7 @@ extern "C" long long vf_group_norm_workspace_floats(int n, int hw, int groups) {
   if (n <= 0 || hw <= 0 || groups <= 0) return 0;
   vf::gn_plan(n, hw, &slabs, &rps);
   (void)slabs;
-  return (long long)n * 64 * groups * 2;      // 64 = the most slabs gn_plan hands out (sample groups re-plan)
+  return (long long)n * 128 * groups * 2;     // 128 = the most slabs any of the slab plans hands out
 }
 
 extern "C" int vf_group_norm_nhwc(const void* x, const void* add_nc, const void* gamma, const void* beta, void* y,
@@ -935,6 +1440,28 @@ extern "C" int vf_group_norm_nhwc_cat(const void* x, int c1, const void* x2, int
   const int rpb_ = kGnThreads / (chunks_ < kGnThreads ? chunks_ : kGnThreads);
   const size_t stats_smem = (size_t)2 * rpb_ * c * sizeof(float);
   if (stats_smem > 48 * 1024) return fail("vf_group_norm_nhwc: c=%d too wide", c);
+  {
+    // Default (VF_GN_FUSED=2): one persistent launch with the slab resident in shared memory; 1 = one launch, second
+    // read out of L2; 0 = the statistics / apply pair.
+    static int fused = -1, slab_kb = -1;
+    if (fused < 0) { const char* e_ = getenv("VF_GN_FUSED"); fused = e_ ? atoi(e_) : 2; }
+    if (slab_kb < 0) { const char* e_ = getenv("VF_GN_SLAB_KB"); slab_kb = e_ ? atoi(e_) : 160; if (slab_kb < 1) slab_kb = 160; }
+    if (fused && chunks_ <= kGnfMaxThreads && n <= kGnfMaxN) {
+      const int tpr = chunks_, rpb = kGnfMaxThreads / tpr;
+      const int threads = (tpr * rpb + 31) / 32 * 32;
+      // fused >= 2 (default): slab resident in shared memory (x crosses HBM once); 1: second read out of L2
+      if (fused >= 2 && c / groups >= e) {
+        const size_t budget = 112 * 1024 - kGnrHeaderBytes - kGnfMaxThreads * sizeof(float4) - 1024;
+        gnr_plan(hw, c, dtype == VF_F32 ? 4 : 2, rpb, budget, &P.slabs, &P.rows_per_slab);
+        if (P.slabs > 0)
+          return dtype == VF_F32 ? gn_resident_launch<float>(P, tpr, rpb, threads, st)
+                                 : gn_resident_launch<__nv_bfloat16>(P, tpr, rpb, threads, st);
+      }
+      gnf_plan(hw, c, dtype == VF_F32 ? 4 : 2, rpb, slab_kb, &P.slabs, &P.rows_per_slab);
+      return dtype == VF_F32 ? gn_fused_launch<float>(P, tpr, rpb, threads, st)
+                             : gn_fused_launch<__nv_bfloat16>(P, tpr, rpb, threads, st);
+    }
+  }
   {
     // Experimental (VF_GN_ONEPASS=1): measured SLOWER than the L2-blocked two-pass below on B200 (0.49 vs
     // 0.24 ms at n=96, 64x64x320 bf16): one 256-thread CTA per SM cannot hide its own shared-memory and MUFU

@@ -324,6 +324,7 @@ def ddim_invert_step(x: torch.Tensor, e_cond: torch.Tensor, a_cur: float, a_next
 
 
 # ---- fused glue kernels of the UNet (vf_norm.cu) ---------------------------------------------------------
+_GN_FUSED = os.environ.get("VF_GN_FUSED", "1") != "0"
 def _rows_c(t: torch.Tensor, name: str):
     if not t.is_contiguous():
         raise ValueError(f"{name}: expected a contiguous (..., c) tensor, got strides {t.stride()}")
@@ -362,7 +363,10 @@ def group_norm_nhwc(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, e
                                     weight.data_ptr(), bias.data_ptr(), y.data_ptr(), ws.data_ptr(), n, hw, groups,
                                     float(eps), int(silu), _code(x), _stream(x))
     _lib.check(rc, "vf_group_norm_nhwc_cat")
-    _count(2)
+    # one persistent launch (vf_norm.cu: gn_fused_kernel) unless the row is wider than 320 16-byte chunks, the batch
+    # exceeds its counter table, or VF_GN_FUSED=0 keeps the statistics / apply pair
+    fused = _GN_FUSED and c * x.element_size() // 16 <= 320 and n <= 4096
+    _count(1 if fused else 2)
     return y
 
 
