@@ -54,6 +54,27 @@ template <> struct V16<__nv_bfloat16> {
   }
 };
 
+// 16 raw bytes -> E/2 register pairs for the packed fp32 pipe (FFMA2 / FADD2), and back
+template <typename T> struct P16;
+template <> struct P16<float> {
+  static __device__ __forceinline__ void unpack(const uint4& u, float2 (&v)[2]) {
+    v[0] = make_float2(__uint_as_float(u.x), __uint_as_float(u.y));
+    v[1] = make_float2(__uint_as_float(u.z), __uint_as_float(u.w));
+  }
+  static __device__ __forceinline__ uint4 pack(const float2 (&v)[2]) {
+    return make_uint4(__float_as_uint(v[0].x), __float_as_uint(v[0].y), __float_as_uint(v[1].x), __float_as_uint(v[1].y));
+  }
+};
+template <> struct P16<__nv_bfloat16> {
+  static __device__ __forceinline__ void unpack(const uint4& u, float2 (&v)[4]) {
+    v[0] = make_float2(bf16lo(u.x), bf16hi(u.x)); v[1] = make_float2(bf16lo(u.y), bf16hi(u.y));
+    v[2] = make_float2(bf16lo(u.z), bf16hi(u.z)); v[3] = make_float2(bf16lo(u.w), bf16hi(u.w));
+  }
+  static __device__ __forceinline__ uint4 pack(const float2 (&v)[4]) {
+    return make_uint4(pack_bf16(v[0].x, v[0].y), pack_bf16(v[1].x, v[1].y), pack_bf16(v[2].x, v[2].y), pack_bf16(v[3].x, v[3].y));
+  }
+};
+
 // SiLU.  fp32 path: IEEE division (reference precision).  bf16 path: the output is rounded to 8 mantissa
 // bits anyway, so the quotient goes through the fast reciprocal (MUFU.RCP) instead of the ~10-instruction
 // IEEE division sequence.
@@ -797,24 +818,25 @@ static int gn_cluster_launch(GnParams& P, int cs, size_t smem, cudaStream_t st) 
 constexpr int kGnrChunks = 8;
 constexpr int kGnrMaxSlabs = 128;
 
+constexpr int kGnrMaxThreads = kGnfMaxThreads;      // 512 threads per CTA (64 registers) measured slower: 0.146 vs 0.141 ms
+
 struct GnrHeader {
   uint64_t bar[kGnrChunks];
   float mean[kGnMaxGroups], rstd[kGnMaxGroups];
-  double red[kGnfMaxThreads / 32][kGnMaxGroups][2];
   int item;
 };
-constexpr int kGnrHeaderBytes = 6 * 1024;
+constexpr int kGnrHeaderBytes = 1024;
 static_assert(sizeof(GnrHeader) <= kGnrHeaderBytes, "header");
 
-template <typename T>
-__global__ void __launch_bounds__(kGnfMaxThreads, 2)
+template <typename T, int kMinB>
+__global__ void __launch_bounds__(kGnfMaxThreads, kMinB)
 gn_resident_kernel(const GnParams P, const int tpr, const int rpb, const int set) {
   constexpr int E = V16<T>::E;
   extern __shared__ __align__(128) unsigned char gnr_smem[];
   GnrHeader* H = reinterpret_cast<GnrHeader*>(gnr_smem);
   float4* s_pair = reinterpret_cast<float4*>(gnr_smem + kGnrHeaderBytes);          // per thread: (sum, sq) of its two groups
-  T* slab1 = reinterpret_cast<T*>(gnr_smem + kGnrHeaderBytes + kGnfMaxThreads * sizeof(float4));
-  unsigned int* sync = g_gn_sync[set];
+  T* slab1 = reinterpret_cast<T*>(gnr_smem + kGnrHeaderBytes + kGnrMaxThreads * sizeof(float4));
+  unsigned int* sync = g_gn_sync[set & 0xff];
   const int tid = threadIdx.x;
   const int my_row = tid / tpr, my_chunk = tid - my_row * tpr;
   const bool active = my_row < rpb;
@@ -834,8 +856,12 @@ gn_resident_kernel(const GnParams P, const int tpr, const int rpb, const int set
     sm100::fence_barrier_init();
   }
   uint32_t phase = 0;
+  // thread 0 takes the ticket of the NEXT item as soon as the current sample is complete (its round trip then hides
+  // under the apply pass).  Not earlier: a ticket held while waiting could belong to the sample being waited for.
+  int next_item = 0;
+  if (tid == 0) next_item = (int)atomicAdd(&sync[0], 1u);
   for (;; phase ^= 1u) {
-    if (tid == 0) H->item = (int)atomicAdd(&sync[0], 1u);
+    if (tid == 0) H->item = next_item;
     __syncthreads();                                    // also: every thread is done with the previous slab
     const int item = H->item;
     if (item >= total) break;
@@ -858,31 +884,36 @@ gn_resident_kernel(const GnParams P, const int tpr, const int rpb, const int set
     }
 
     // parameters of phase 2 now: their latency hides under the slab load instead of sitting behind the sample wait
-    float gam[E], bet[E], av[E];
+    float av[E];
 #pragma unroll
-    for (int j = 0; j < E; ++j) { gam[j] = 0.f; bet[j] = 0.f; av[j] = 0.f; }
-    if (active) {
-      V16<T>::ld(reinterpret_cast<const T*>(P.gamma) + ch, gam);
-      V16<T>::ld(reinterpret_cast<const T*>(P.beta) + ch, bet);
-      if (P.add_nc) V16<T>::ld(reinterpret_cast<const T*>(P.add_nc) + (size_t)n * P.c + ch, av);
-    }
+    for (int j = 0; j < E; ++j) av[j] = 0.f;
+    if (active && P.add_nc) V16<T>::ld(reinterpret_cast<const T*>(P.add_nc) + (size_t)n * P.c + ch, av);
 
-    // ---- phase 1: statistics as the chunks land --------------------------------------------------------
+    // ---- phase 1: statistics as the chunks land (packed fp32 pairs: FADD2 / FFMA2) ---------------------
     {
       float sum[E], sq[E];
+      {
+        float2 sum2[E / 2], sq2[E / 2];
 #pragma unroll
-      for (int j = 0; j < E; ++j) { sum[j] = 0.f; sq[j] = 0.f; }
-      int r = my_row;
-      for (int kc = 0; kc < kGnrChunks; ++kc) {
-        sm100::mbar_wait(&H->bar[kc], phase);
-        const int b = min(nrows, (kc + 1) * rows_per_chunk);
-        if (active) {
-          for (; r < b; r += rpb) {
-            float v[E];
-            V16<T>::ld(my_slab + (size_t)r * ld, v);
+        for (int j = 0; j < E / 2; ++j) { sum2[j] = make_float2(0.f, 0.f); sq2[j] = make_float2(0.f, 0.f); }
+        int r = my_row;
+        for (int kc = 0; kc < kGnrChunks; ++kc) {
+          sm100::mbar_wait(&H->bar[kc], phase);
+          const int b = min(nrows, (kc + 1) * rows_per_chunk);
+          if (active) {
+#pragma unroll 4
+            for (; r < b; r += rpb) {
+              float2 v[E / 2];
+              P16<T>::unpack(*reinterpret_cast<const uint4*>(my_slab + (size_t)r * ld), v);
 #pragma unroll
-            for (int j = 0; j < E; ++j) { sum[j] += v[j]; sq[j] = fmaf(v[j], v[j], sq[j]); }
+              for (int j = 0; j < E / 2; ++j) { sum2[j] = __fadd2_rn(sum2[j], v[j]); sq2[j] = __ffma2_rn(v[j], v[j], sq2[j]); }
+            }
           }
+        }
+#pragma unroll
+        for (int j = 0; j < E / 2; ++j) {
+          sum[2 * j] = sum2[j].x; sum[2 * j + 1] = sum2[j].y;
+          sq[2 * j] = sq2[j].x; sq[2 * j + 1] = sq2[j].y;
         }
       }
       if (active) {
@@ -931,11 +962,14 @@ gn_resident_kernel(const GnParams P, const int tpr, const int rpb, const int set
     }
     __syncthreads();
     if (tid == 0) {
-      __threadfence();
-      atomicAdd(&sync[2 + 2 * n], 1u);
-      while (ld_acquire_u32(&sync[2 + 2 * n]) < (unsigned)P.slabs) __nanosleep(64);
-      const unsigned d = atomicAdd(&sync[3 + 2 * n], 1u);
-      if (d == (unsigned)P.slabs - 1u) { sync[2 + 2 * n] = 0u; sync[3 + 2 * n] = 0u; }
+      // release: the CTA's partials (ordered before this thread by the barrier) become visible with the arrival
+      unsigned seen;
+      asm volatile("atom.add.release.gpu.global.u32 %0, [%1], 1;" : "=r"(seen) : "l"(&sync[2 + 2 * n]) : "memory");
+      if (seen + 1u < (unsigned)P.slabs && !(set & 0x100))          // 0x100: VF_GN_DEBUG_NOWAIT (timing experiment, wrong results)
+        while (ld_acquire_u32(&sync[2 + 2 * n]) < (unsigned)P.slabs) __nanosleep(32);
+      else
+        asm volatile("fence.acq_rel.gpu;" ::: "memory");
+      next_item = (int)atomicAdd(&sync[0], 1u);
     }
     __syncthreads();
     // totals of the sample: eight lanes per group, slabs strided over the lanes (their loads go out together: one L2
@@ -973,33 +1007,60 @@ gn_resident_kernel(const GnParams P, const int tpr, const int rpb, const int set
 
     // ---- phase 2: apply out of shared memory --------------------------------------------------------------
     if (active) {
-      float scale[E], shift[E];
+      float scale[E], shift[E], gam[E], bet[E];          // gamma / beta: the same lines every item, L1 hits
+      V16<T>::ld(reinterpret_cast<const T*>(P.gamma) + ch, gam);
+      V16<T>::ld(reinterpret_cast<const T*>(P.beta) + ch, bet);
 #pragma unroll
       for (int j = 0; j < E; ++j) {
         const int grp = (ch + j) / cpg;
         scale[j] = H->rstd[grp] * gam[j];
         shift[j] = fmaf(av[j] - H->mean[grp], scale[j], bet[j]);
       }
+      // bf16 SiLU = h + h tanh(h), h = t / 2: the 1/2 is folded into scale / shift, the rest is two packed FMAs per pair
+      constexpr bool kBf = sizeof(T) == 2;
+      const float ks = (kBf && P.silu) ? 0.5f : 1.0f;
+      float2 scale2[E / 2], shift2[E / 2];
+#pragma unroll
+      for (int j = 0; j < E / 2; ++j) {
+        scale2[j] = make_float2(scale[2 * j] * ks, scale[2 * j + 1] * ks);
+        shift2[j] = make_float2(shift[2 * j] * ks, shift[2 * j + 1] * ks);
+      }
       char* q = reinterpret_cast<char*>(reinterpret_cast<T*>(P.y) + ((size_t)n * P.hw + r0 + my_row) * P.c + ch);
       const size_t qstride = (size_t)rpb * P.c * sizeof(T);
 #pragma unroll 4
       for (int r = my_row; r < nrows; r += rpb, q += qstride) {
-        float v[E];
-        V16<T>::ld(my_slab + (size_t)r * ld, v);
+        float2 v[E / 2];
+        P16<T>::unpack(*reinterpret_cast<const uint4*>(my_slab + (size_t)r * ld), v);
 #pragma unroll
-        for (int j = 0; j < E; ++j) {
-          float t = fmaf(v[j], scale[j], shift[j]);
-          if (P.silu) t = silu_f<T>(t);
+        for (int j = 0; j < E / 2; ++j) {
+          float2 t = __ffma2_rn(v[j], scale2[j], shift2[j]);
+          if (P.silu) {
+            if constexpr (kBf) {
+              float2 th;
+              asm("tanh.approx.f32 %0, %1;" : "=f"(th.x) : "f"(t.x));
+              asm("tanh.approx.f32 %0, %1;" : "=f"(th.y) : "f"(t.y));
+              t = __ffma2_rn(t, th, t);
+            } else {
+              t = make_float2(silu_f<T>(t.x), silu_f<T>(t.y));
+            }
+          }
           v[j] = t;
         }
-        st_na_v4(q, V16<T>::pack(v));
+        st_na_v4(q, P16<T>::pack(v));
       }
     }
   }
+  // the last CTA out re-arms the set: ticket, exit count and the arrival counters of all samples (every CTA has
+  // left its loop by then, nobody reads them any more)
+  __syncthreads();
   if (tid == 0) {
     __threadfence();
-    const unsigned f = atomicAdd(&sync[1], 1u);
-    if (f == gridDim.x - 1u) { sync[0] = 0u; sync[1] = 0u; }
+    H->item = (int)atomicAdd(&sync[1], 1u);
+  }
+  __syncthreads();
+  if (H->item == (int)gridDim.x - 1) {
+    for (int i = tid; i < P.n; i += blockDim.x) sync[2 + 2 * i] = 0u;
+    if (tid == 0) { sync[0] = 0u; sync[1] = 0u; }
   }
 }
 
@@ -1017,21 +1078,31 @@ static void gnr_plan(int hw, int c, int esize, int rpb, size_t budget, int* slab
   *rows_per_slab = (int)rows;
 }
 
-template <typename T>
-static int gn_resident_launch(GnParams& P, int tpr, int rpb, int threads, cudaStream_t st) {
+// Two CTAs per SM, ~100 KB slabs (three with ~64 KB slabs measured slower: 0.152 vs 0.135 ms at 96 x 4096 x 320 -- the
+// per-item synchronisation is amortised over fewer bytes).
+static size_t gnr_smem_per_cta() { return 112 * 1024; }
+
+template <typename T, int kMinB>
+static int gn_resident_launch_t(GnParams& P, int tpr, int rpb, int threads, cudaStream_t st) {
   static unsigned launch_no = 0;
   const int set = (int)(launch_no++ % kGnSyncSets);
-  const size_t smem = kGnrHeaderBytes + kGnfMaxThreads * sizeof(float4) + (size_t)P.rows_per_slab * P.c * sizeof(T);
-  static size_t attr = 0;
-  if (smem > attr) {
-    VF_CUDA_TRY(cudaFuncSetAttribute(gn_resident_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
-    attr = 112 * 1024;
+  const size_t smem = kGnrHeaderBytes + kGnrMaxThreads * sizeof(float4) + (size_t)P.rows_per_slab * P.c * sizeof(T);
+  static bool attr = false;
+  if (!attr) {
+    VF_CUDA_TRY(cudaFuncSetAttribute(gn_resident_kernel<T, kMinB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gnr_smem_per_cta()));
+    attr = true;
   }
   long long grid = (long long)P.n * P.slabs;
-  const long long cap = 2LL * num_sms();
+  const long long cap = (long long)kMinB * num_sms();
   if (grid > cap) grid = cap;
-  gn_resident_kernel<T><<<(int)grid, threads, smem, st>>>(P, tpr, rpb, set);
+  static int nowait = -1;
+  if (nowait < 0) { const char* e_ = getenv("VF_GN_DEBUG_NOWAIT"); nowait = e_ ? atoi(e_) : 0; }
+  gn_resident_kernel<T, kMinB><<<(int)grid, threads, smem, st>>>(P, tpr, rpb, set | (nowait ? 0x100 : 0));
   return check_cuda(cudaGetLastError(), "gn_resident_kernel launch");
+}
+template <typename T>
+static int gn_resident_launch(GnParams& P, int tpr, int rpb, int threads, cudaStream_t st) {
+  return gn_resident_launch_t<T, 2>(P, tpr, rpb, threads, st);
 }
 
 // ================================================================================================
@@ -1451,11 +1522,16 @@ extern "C" int vf_group_norm_nhwc_cat(const void* x, int c1, const void* x2, int
       const int threads = (tpr * rpb + 31) / 32 * 32;
       // fused >= 2 (default): slab resident in shared memory (x crosses HBM once); 1: second read out of L2
       if (fused >= 2 && c / groups >= e) {
-        const size_t budget = 112 * 1024 - kGnrHeaderBytes - kGnfMaxThreads * sizeof(float4) - 1024;
-        gnr_plan(hw, c, dtype == VF_F32 ? 4 : 2, rpb, budget, &P.slabs, &P.rows_per_slab);
+        static int res_threads = -1;                    // VF_GN_RES_THREADS: most threads per CTA (multiple of 32, <= 512)
+        if (res_threads < 0) { const char* e_ = getenv("VF_GN_RES_THREADS"); res_threads = e_ ? atoi(e_) : kGnrMaxThreads; if (res_threads < 32 || res_threads > kGnrMaxThreads) res_threads = kGnrMaxThreads; }
+        const int mt = res_threads < tpr ? tpr : res_threads;
+        const int rpb_r = mt / tpr;
+        const int threads_r = (tpr * rpb_r + 31) / 32 * 32;
+        const size_t budget = gnr_smem_per_cta() - kGnrHeaderBytes - kGnrMaxThreads * sizeof(float4);
+        gnr_plan(hw, c, dtype == VF_F32 ? 4 : 2, rpb_r, budget, &P.slabs, &P.rows_per_slab);
         if (P.slabs > 0)
-          return dtype == VF_F32 ? gn_resident_launch<float>(P, tpr, rpb, threads, st)
-                                 : gn_resident_launch<__nv_bfloat16>(P, tpr, rpb, threads, st);
+          return dtype == VF_F32 ? gn_resident_launch<float>(P, tpr, rpb_r, threads_r, st)
+                                 : gn_resident_launch<__nv_bfloat16>(P, tpr, rpb_r, threads_r, st);
       }
       gnf_plan(hw, c, dtype == VF_F32 ? 4 : 2, rpb, slab_kb, &P.slabs, &P.rows_per_slab);
       return dtype == VF_F32 ? gn_fused_launch<float>(P, tpr, rpb, threads, st)
