@@ -39,10 +39,18 @@ constexpr int kGemmThreads = 384;     // warp 0 TMA, 1 MMA, 2-3 idle, 4-7 epilog
 constexpr int kGemmBM = 128;          // rows per tile
 constexpr int kGemmBN = 128;          // OUTPUT columns per tile (256 accumulator columns: value + gate)
 constexpr int kGemmBK = 64;           // k-block: 64 bf16 = one 128-byte swizzled row
-constexpr int kGemmStages = 4;
+constexpr int kGemmStages = 4;        // ring depth of the streaming kernel (A + W per stage)
+constexpr int kGemmStagesRes = 3;     // ring depth of the W-resident kernel (A only): the fourth stage's 16 KB hold the output staging
 constexpr uint32_t kATileBytes = kGemmBM * kGemmBK * 2;          // 16 KB
 constexpr uint32_t kBTileBytes = 2 * kGemmBN * kGemmBK * 2;      // 32 KB (value rows, then gate rows)
 constexpr uint32_t kStageBytes = kATileBytes + kBTileBytes;
+// Output staging: one column step (128 rows x 32 bf16 = 64-byte rows, 64B-swizzled) per buffer, written by the
+// epilogue threads and drained by a TMA store.  A thread owns a ROW of the accumulator (TMEM lane), so storing
+// straight from registers made every 16-byte store instruction touch 32 different rows: 2048 l1tex wavefronts per
+// tile, 66 % of the LSU data pipe (profiles/r1_geglu_gemm_ncu.txt) -- the same order as the tile's 2560 tensor cycles.
+// Through the staging buffer a warp's store is 4 conflict-free shared-memory wavefronts and the global write is the
+// TMA engine's.
+constexpr uint32_t kStageOutBytes = kGemmBM * 32 * 2;            // 8 KB
 
 struct GemmGegluParams {
   __nv_bfloat16* out;
@@ -50,6 +58,7 @@ struct GemmGegluParams {
   long long rows;
   int n, k;
   int m_blocks, n_blocks, k_blocks;
+  int prefetch;                    // W-resident: L2 prefetch distance of one tile (VF_GEMM_PREFETCH, default on)
 };
 
 struct __align__(8) GemmBarriers {
@@ -91,6 +100,11 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       :: "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+// L2 prefetch of a tile (no shared-memory destination, no completion tracking)
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* m, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];"
+               :: "l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1) : "memory");
+}
 __device__ __forceinline__ void named_bar_sync(int id, int threads) {
   asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(threads) : "memory");
 }
@@ -129,33 +143,38 @@ __device__ __forceinline__ float2 geglu_pair(float2 v, float2 g) {
   return __fmul2_rn(v, __ffma2_rn(hg, sg, hg));
 }
 
-template <bool kWResident>
+template <bool kWResident, int kEpiGroups>      // kEpiGroups: 1 = four epilogue warps (4-7), 2 = eight (4-11)
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_geglu_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
-                  const GemmGegluParams P) {
+                  const __grid_constant__ CUtensorMap map_o, const GemmGegluParams P) {
   // all shared memory is dynamic (the W-resident layout uses the 227 KB to within 1 KB):
-  //   [pad to 1024] | resident W (k_blocks x 32 KB, W-resident only) | ring (kGemmStages stages) | barriers | bias
+  //   [pad to 1024] | resident W (k_blocks x 32 KB, W-resident only) | ring | output staging | barriers | bias
   extern __shared__ unsigned char gemm_smem[];
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const uint32_t dyn_base = smem_u32(gemm_smem);
   const uint32_t tile_base = (dyn_base + 1023u) & ~1023u;
   unsigned char* tiles = gemm_smem + (tile_base - dyn_base);
-  const size_t tile_bytes = (kWResident ? (size_t)P.k_blocks * kBTileBytes + (size_t)kGemmStages * kATileBytes
-                                        : (size_t)kGemmStages * kStageBytes);
+  constexpr int kStages = kWResident ? kGemmStagesRes : kGemmStages;
+  constexpr int kOutBufs = (kWResident && kEpiGroups == 1) ? 2 : 1;     // staging buffers per epilogue group: 16 KB in all
+  constexpr int kEpiGroupsC = kEpiGroups;
+  const size_t ring_bytes = (kWResident ? (size_t)P.k_blocks * kBTileBytes + (size_t)kStages * kATileBytes
+                                        : (size_t)kStages * kStageBytes);
+  unsigned char* out_stage = tiles + ring_bytes;          // 1024-aligned: every part before it is a multiple of 1 KB
+  const size_t tile_bytes = ring_bytes + (size_t)kEpiGroupsC * kOutBufs * kStageOutBytes;
   GemmBarriers& bars = *reinterpret_cast<GemmBarriers*>(tiles + tile_bytes);
   // per accumulator set: value bias [0,128), gate bias [128,256)
   float (*s_bias)[2 * kGemmBN] = reinterpret_cast<float (*)[2 * kGemmBN]>(tiles + tile_bytes + 128);
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kGemmStages; ++s) {
+    for (int s = 0; s < kStages; ++s) {
       mbar_init(&bars.full[s], 1);
       mbar_init(&bars.empty[s], 1);
     }
     mbar_init(&bars.w_full, 1);
     for (int a = 0; a < 2; ++a) {
       mbar_init(&bars.acc_full[a], 1);
-      mbar_init(&bars.acc_empty[a], kWResident ? 4 : 8);            // one arrival per epilogue warp
+      mbar_init(&bars.acc_empty[a], 4 * kEpiGroups);                // one arrival per epilogue warp
     }
     fence_barrier_init();
   }
@@ -174,6 +193,7 @@ gemm_geglu_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     if (lane == 0) {
       tma_prefetch_desc(&map_a);
       tma_prefetch_desc(&map_w);
+      tma_prefetch_desc(&map_o);
       uint32_t it = 0;
       TileWalk<kWResident> tw(P);
       if (kWResident && tw.valid()) {
@@ -187,12 +207,19 @@ gemm_geglu_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       for (; tw.valid(); tw.next()) {
         const int mb = tw.mb(), nb = tw.nb();
         for (int kb = 0; kb < P.k_blocks; ++kb, ++it) {
-          const int s = it % kGemmStages;
-          const uint32_t use = it / kGemmStages;
+          const int s = it % kStages;
+          const uint32_t use = it / kStages;
           mbar_wait(&bars.empty[s], (use & 1) ^ 1);
           mbar_arrive_expect_tx(&bars.full[s], kRingStage);
           unsigned char* st = ring + (size_t)s * kRingStage;
           tma_load_2d(st, &map_a, &bars.full[s], kb * kGemmBK, mb * kGemmBM);
+          // W-resident: the ring holds 48 KB per SM, i.e. 48 KB per memory latency -- with A coming from HBM (~1.2 us
+          // under load) that is ~17 B/clk/SM, half of what the tile's 2560 tensor cycles need.  Pull the same k-block
+          // of the NEXT tile into L2 now, so that its load is an L2 hit when its turn comes.
+          if (kWResident && (P.prefetch & 1) && tw.cur + tw.step < tw.end)
+            tma_prefetch_2d(&map_a, kb * kGemmBK, (int)(tw.cur + tw.step) * kGemmBM);
+          if (!kWResident && (P.prefetch & 2) && tw.cur + tw.step < tw.end)            // streaming: next tile's A row block
+            tma_prefetch_2d(&map_a, kb * kGemmBK, (int)((tw.cur + tw.step) / tw.n_blocks) * kGemmBM);
           if (!kWResident) {
             tma_load_2d(st + kATileBytes, &map_w, &bars.full[s], kb * kGemmBK, nb * kGemmBN);
             tma_load_2d(st + kATileBytes + kBTileBytes / 2, &map_w, &bars.full[s], kb * kGemmBK, P.n + nb * kGemmBN);
@@ -216,8 +243,8 @@ gemm_geglu_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         tc_fence_after();
         const uint32_t acc = tmem + ab * (2 * kGemmBN);
         for (int kb = 0; kb < P.k_blocks; ++kb, ++it) {
-          const int s = it % kGemmStages;
-          mbar_wait(&bars.full[s], (it / kGemmStages) & 1);
+          const int s = it % kStages;
+          mbar_wait(&bars.full[s], (it / kStages) & 1);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(ring + (size_t)s * kRingStage);
           const uint32_t b_addr = kWResident ? smem_u32(w_res + (size_t)kb * kBTileBytes) : a_addr + kATileBytes;
@@ -232,18 +259,17 @@ gemm_geglu_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         tc_commit(&bars.acc_full[ab]);
       }
     }
-  } else if (warp >= 4 && (!kWResident || warp < 8)) {
+  } else if (warp >= 4 && warp < 4 + 4 * kEpiGroups) {
     // =========================== epilogue ========================================================
     // Eight epilogue warps: warps 4-7 and 8-11 both cover the four TMEM lane quarters (a warp may touch quarter
     // warp % 4) and split the column steps of every tile.  With four, ONE warp per scheduler had to push the ~12
     // issue slots per output element at single-warp IPC.  Measured: k = 640 0.567 -> 0.539 ms, k = 1280 0.480 -> 0.465;
     // the W-resident kernel (k = 320) got SLOWER with eight (0.659 -> 0.739 ms) and keeps four.
-    constexpr int kEpiGroups = kWResident ? 1 : 2;
     const int quarter = warp & 3;
     const int ehalf = (warp - 4) >> 2;                       // group 0: the first half of the column steps, 1: the rest
     const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
     const int et = threadIdx.x - 128;                        // 0..255; the first 128 stage the bias
-    uint32_t ti = 0;
+    uint32_t ti = 0, ostep = 0;
     for (TileWalk<kWResident> tw(P); tw.valid(); tw.next(), ++ti) {
       const int mb = tw.mb(), nb = tw.nb();
       const uint32_t ab = ti & 1, ause = ti >> 1;
@@ -261,10 +287,9 @@ gemm_geglu_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       mbar_wait(&bars.acc_full[ab], ause & 1);
       tc_fence_after();
       const uint32_t acc = tmem + ab * (2 * kGemmBN) + lane_off;
-      const long long row = (long long)mb * kGemmBM + quarter * 32 + lane;
-      __nv_bfloat16* orow = P.out + row * P.n + (long long)nb * kGemmBN;
+      const int trow = quarter * 32 + lane;                  // row of the tile this thread owns
 #pragma unroll 1
-      for (int c = ehalf * (kGemmBN / 32 / kEpiGroups); c < (ehalf + 1) * (kGemmBN / 32 / kEpiGroups); ++c) {
+      for (int c = ehalf * (kGemmBN / 32 / kEpiGroups); c < (ehalf + 1) * (kGemmBN / 32 / kEpiGroups); ++c, ++ostep) {
         uint32_t v[32], g[32];
         tmem_ld_x32(acc + c * 32, v);
         tmem_ld_x32(acc + kGemmBN + c * 32, g);
@@ -282,16 +307,35 @@ gemm_geglu_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
           pk[i / 2] = pack_bf16(oa.x, oa.y);
           pk[i / 2 + 1] = pack_bf16(ob.x, ob.y);
         }
-        if (row < P.rows) {
+        // 64-byte row of this step into the staging buffer, TMA's 64B swizzle: 16-byte chunk q of row r sits at
+        // chunk q ^ ((r >> 1) & 3) -- eight consecutive rows cover all 32 banks, 4 wavefronts per warp instruction.
+        unsigned char* obuf = out_stage + (size_t)(ehalf * kOutBufs + (kOutBufs == 2 ? (ostep & 1) : 0)) * kStageOutBytes;
+        const uint32_t sw = (uint32_t)(trow >> 1) & 3u;
+        const bool issuer = (threadIdx.x & 127) == 0;
+        if (kOutBufs == 1) {                                   // single buffer: the previous step's store must have drained it
+          if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          named_bar_sync(2 + ehalf, 128);
+        }
 #pragma unroll
-          for (int q = 0; q < 4; ++q)
-            *reinterpret_cast<uint4*>(orow + c * 32 + q * 8) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+        for (int q = 0; q < 4; ++q)
+          *reinterpret_cast<uint4*>(obuf + trow * 64 + ((q ^ sw) << 4)) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+        fence_proxy_async();
+        // the issuing thread first makes sure the OTHER buffer (written next) has been drained by its store, then the
+        // group meets, then this buffer goes out: one barrier per step
+        if (kOutBufs == 2 && issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        named_bar_sync(2 + ehalf, 128);
+        if (issuer) {
+          asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
+                       :: "l"(reinterpret_cast<uint64_t>(&map_o)), "r"(nb * kGemmBN + c * 32), "r"(mb * kGemmBM), "r"(smem_u32(obuf))
+                       : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars.acc_empty[ab]);
     }
+    if ((threadIdx.x & 127) == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");     // stores complete before exit
   }
 
   __syncthreads();
@@ -332,6 +376,20 @@ static int make_map_2d(CUtensorMap* m, const void* base, long long rows, int k, 
   return 0;
 }
 
+// output (rows, n) bf16 row-major -> 2-D map {n, rows}, box {32, 128}, 64B swizzle (the staging layout of the epilogue)
+static int make_map_out(CUtensorMap* m, void* base, long long rows, int n, const char* who) {
+  EncodeTiledFn2 enc = gemm_encode_fn();
+  if (!enc) return fail("%s: cuTensorMapEncodeTiled entry point not found", who);
+  cuuint64_t dims[2] = {(cuuint64_t)n, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)n * 2};
+  cuuint32_t box[2] = {32, (cuuint32_t)kGemmBM};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail("%s: cuTensorMapEncodeTiled (output) failed with CUresult %d", who, (int)r);
+  return 0;
+}
+
 }  // namespace vf
 
 extern "C" int vf_linear_geglu(const void* x, const void* w, const void* bias, void* out,
@@ -346,9 +404,10 @@ extern "C" int vf_linear_geglu(const void* x, const void* w, const void* bias, v
   const void* ptrs[3] = {x, w, out};
   for (const void* p : ptrs)
     if (reinterpret_cast<uintptr_t>(p) & 15) return fail("vf_linear_geglu: pointers must be 16-byte aligned");
-  CUtensorMap ma, mw;
+  CUtensorMap ma, mw, mo;
   if (int rc = make_map_2d(&ma, x, rows, k, ld_x, "vf_linear_geglu")) return rc;
   if (int rc = make_map_2d(&mw, w, 2LL * n, k, k, "vf_linear_geglu")) return rc;
+  if (int rc = make_map_out(&mo, out, rows, n, "vf_linear_geglu")) return rc;
   GemmGegluParams P;
   P.out = reinterpret_cast<__nv_bfloat16*>(out);
   P.bias = reinterpret_cast<const __nv_bfloat16*>(bias);
@@ -360,26 +419,35 @@ extern "C" int vf_linear_geglu(const void* x, const void* w, const void* bias, v
   if (w_res_knob < 0) { const char* e = getenv("VF_GEMM_WRES"); w_res_knob = e ? atoi(e) : 1; }
   constexpr size_t kTail = 128 + 2 * 2 * kGemmBN * sizeof(float);      // barriers + bias
   static_assert(sizeof(GemmBarriers) <= 128, "barrier block");
-  const size_t smem_res = 1008 + (size_t)P.k_blocks * kBTileBytes + (size_t)kGemmStages * kATileBytes + 128 + 2 * kGemmBN * sizeof(float);
+  static int pf_knob = -1;
+  if (pf_knob < 0) { const char* e = getenv("VF_GEMM_PREFETCH"); pf_knob = e ? atoi(e) : 1; }
+  P.prefetch = pf_knob;
+  static int epi_res = -1;         // VF_GEMM_EPI_RES: epilogue warp groups of the W-resident kernel (1 or 2)
+  if (epi_res < 0) { const char* e = getenv("VF_GEMM_EPI_RES"); epi_res = e ? atoi(e) : 2; if (epi_res != 1) epi_res = 2; }
+  const size_t smem_res = 1008 + (size_t)P.k_blocks * kBTileBytes + (size_t)kGemmStagesRes * kATileBytes + 2 * kStageOutBytes +
+                          128 + 2 * kGemmBN * sizeof(float);
   const bool resident = w_res_knob && smem_res <= 232448 && P.n_blocks <= num_sms() && P.m_blocks >= 4 * (num_sms() / P.n_blocks);
   if (resident) {
     static size_t attr_r = 0;
     if (smem_res > attr_r) {
-      VF_CUDA_TRY(cudaFuncSetAttribute(gemm_geglu_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_res));
+      VF_CUDA_TRY(cudaFuncSetAttribute(gemm_geglu_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_res));
+      VF_CUDA_TRY(cudaFuncSetAttribute(gemm_geglu_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_res));
       attr_r = smem_res;
     }
     const int groups = num_sms() / P.n_blocks;
-    gemm_geglu_kernel<true><<<groups * P.n_blocks, 256, smem_res, (cudaStream_t)stream>>>(ma, mw, P);
+    if (epi_res == 1) gemm_geglu_kernel<true, 1><<<groups * P.n_blocks, 256, smem_res, (cudaStream_t)stream>>>(ma, mw, mo, P);
+    else gemm_geglu_kernel<true, 2><<<groups * P.n_blocks, kGemmThreads, smem_res, (cudaStream_t)stream>>>(ma, mw, mo, P);
     return check_cuda(cudaGetLastError(), "gemm_geglu_kernel<resident W> launch");
   }
-  const size_t smem = 1008 + (size_t)kGemmStages * kStageBytes + kTail;
+  const size_t smem = 1008 + (size_t)kGemmStages * kStageBytes + 2 * kStageOutBytes + kTail;
+  static_assert(1008 + (size_t)kGemmStages * kStageBytes + 2 * kStageOutBytes + kTail <= 232448, "streaming kernel shared memory");
   static bool attr = false;
   if (!attr) {
-    VF_CUDA_TRY(cudaFuncSetAttribute(gemm_geglu_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    VF_CUDA_TRY(cudaFuncSetAttribute(gemm_geglu_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = true;
   }
   long long grid = (long long)P.m_blocks * P.n_blocks;
   if (grid > num_sms()) grid = num_sms();
-  gemm_geglu_kernel<false><<<(int)grid, kGemmThreads, smem, (cudaStream_t)stream>>>(ma, mw, P);
+  gemm_geglu_kernel<false, 2><<<(int)grid, kGemmThreads, smem, (cudaStream_t)stream>>>(ma, mw, mo, P);
   return check_cuda(cudaGetLastError(), "gemm_geglu_kernel launch");
 }
