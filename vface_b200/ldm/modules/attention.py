@@ -114,7 +114,8 @@ class CrossAttention(nn.Module):
         if ep is not None and not ep.done and a.dtype == torch.bfloat16 and a.dim() == 3 and a.shape[1] >= 256:
             lin = self.to_out[0]
             ep.done = True
-            return ops.linear_residual(a.contiguous(), lin.weight, (lin.bias + ep.row).contiguous(), ep.residual)
+            bias = ep.row if ep.prebiased else (lin.bias + ep.row).contiguous()
+            return ops.linear_residual(a.contiguous(), lin.weight, bias, ep.residual)
         return self.to_out(a)
 
     def single_token_row(self, context):
@@ -143,11 +144,12 @@ _FUSE_TO_OUT = _os.environ.get("VF_FUSE_TO_OUT", "1") != "0"     # tuning knob: 
 
 
 class _FusedOut:
-    """Epilogue armed by BasicTransformerBlock around its attn1 call (see CrossAttention.project_out)."""
-    __slots__ = ("residual", "row", "done")
+    """Epilogue armed by BasicTransformerBlock around its attn1 call (see CrossAttention.project_out).
+    `prebiased`: `row` already contains attn1's to_out bias (BasicTransformerBlock._row_plus_out_bias)."""
+    __slots__ = ("residual", "row", "done", "prebiased")
 
-    def __init__(self, residual, row):
-        self.residual, self.row, self.done = residual, row, False
+    def __init__(self, residual, row, prebiased=False):
+        self.residual, self.row, self.done, self.prebiased = residual, row, False, prebiased
 
 
 class BasicTransformerBlock(nn.Module):
@@ -166,6 +168,27 @@ class BasicTransformerBlock(nn.Module):
     def forward(self, x, context=None):
         return self._forward(x, context)
 
+    def _row_plus_out_bias(self, context):
+        """attn2's single-token row (to_out(to_v(ctx)), CrossAttention.single_token_row) PLUS attn1's to_out bias as ONE small
+        GEMM: to_v has no bias and nothing sits between the two projections, so W = W_out2 W_v (formed in fp32, cached
+        until a parameter changes) and b = b_out2 + b_out1.  Replaces two GEMMs, a bias add and a copy per block and step;
+        bf16 only (one rounding of the row instead of two).  None when the modules are not the plain reference ones."""
+        a1o, a2 = self.attn1.to_out[0], self.attn2
+        a2o = a2.to_out[0]
+        if (type(a1o) is not nn.Linear or type(a2o) is not nn.Linear or type(a2.to_v) is not nn.Linear
+                or a2.to_v.bias is not None or a1o.bias is None or a2o.bias is None):
+            return None
+        ps = (a2.to_v.weight, a2o.weight, a2o.bias, a1o.bias)
+        key = tuple((p.data_ptr(), p._version, p.dtype, p.device) for p in ps)
+        hit = self.__dict__.get("_row_gemm")
+        if hit is None or hit[0] != key:
+            with torch.no_grad():
+                w = (a2o.weight.float() @ a2.to_v.weight.float()).to(a2o.weight.dtype).contiguous()
+                b = (a2o.bias.float() + a1o.bias.float()).to(a2o.bias.dtype).contiguous()
+            hit = (key, w, b)
+            self.__dict__["_row_gemm"] = hit
+        return F.linear(context[:, 0], hit[1], hit[2])
+
     def _forward(self, x, context=None):
         """x = attn1(LN1(x)) + x ; x = attn2(LN2(x), ctx) + x ; x = ff(LN3(x)) + x   (reference :239-243),
         with each residual add fused into the following LayerNorm (one pass instead of two)."""
@@ -179,8 +202,14 @@ class BasicTransformerBlock(nn.Module):
             # attn2's output does not depend on its queries: LN2 is dead and both adds fold into one pass.  bf16: that
             # pass is the to_out GEMM of attn1 itself (x + to_out(a) + b + row in its epilogue, one rounding of the
             # stream); otherwise the LN3 kernel adds a1 and the row while it normalises.
-            row = self.attn2.single_token_row(context)[:, 0]
-            ep = _FusedOut(x, row) if (x.dtype == torch.bfloat16 and _FUSE_TO_OUT) else None
+            row = ep = None
+            if x.dtype == torch.bfloat16 and _FUSE_TO_OUT:
+                row_b = self._row_plus_out_bias(context)
+                if row_b is not None:
+                    ep = _FusedOut(x, row_b, prebiased=True)
+                else:
+                    row = self.attn2.single_token_row(context)[:, 0]
+                    ep = _FusedOut(x, row)
             self.attn1._fused_out = ep
             try:
                 a1 = self.attn1(ln(self.norm1, x))
@@ -190,6 +219,8 @@ class BasicTransformerBlock(nn.Module):
                 x = a1                                      # already x + attn1 + attn2
                 n3 = ln(self.norm3, x)
             else:
+                if row is None:
+                    row = self.attn2.single_token_row(context)[:, 0]
                 x, n3 = ln(self.norm3, x, y=a1.contiguous(), row_bias=row)
             return self._ff_residual(x, n3)
         a1 = self.attn1(ln(self.norm1, x))

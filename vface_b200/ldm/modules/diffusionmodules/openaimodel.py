@@ -120,6 +120,29 @@ class ResBlock(TimestepBlock):
             self._skip_split_key = key
         return self._skip_split
 
+    @staticmethod
+    def _bias_sum(owner, name, a, b):
+        """a + b of two bias parameters, cached on `owner` until either changes (one tiny add kernel per block and step
+        otherwise: a 32-frame step launched ~60 of them)."""
+        key = (a.data_ptr(), a._version, b.data_ptr(), b._version, a.dtype, a.device)
+        hit = owner.__dict__.get(name)
+        if hit is None or hit[0] != key:
+            hit = (key, (a.detach() + b.detach()).contiguous())
+            owner.__dict__[name] = hit
+        return hit[1]
+
+    def _emb_plus_conv_bias(self, emb, conv1):
+        """emb_layers(emb) + conv1.bias (reference :265-273: `h = in_layers(x)`'s bias and `h + emb_out`): the two biases
+        are summed once, and SiLU(emb) -- the same tensor for every ResBlock of a forward -- is taken from the cache
+        UNetModel.forward leaves on `emb`."""
+        act, lin = self.emb_layers[0], self.emb_layers[1]
+        if type(act) is not nn.SiLU or type(lin) is not nn.Linear or lin.bias is None or conv1.bias is None:
+            return self.emb_layers(emb) + conv1.bias
+        se = getattr(emb, "_vf_silu", None)
+        if se is None:
+            se = F.silu(emb)
+        return F.linear(se, lin.weight, self._bias_sum(self, "_emb_conv_bias", lin.bias, conv1.bias))
+
     def _forward(self, x, emb):
         """GN-SiLU-conv, + emb, GN-SiLU-conv, + skip (reference :255-275) on channels-last activations:
         the two GroupNorm+SiLU are one fused kernel each, the `+ emb_out` and the first conv bias ride
@@ -136,7 +159,7 @@ class ResBlock(TimestepBlock):
         gn2, conv2 = self.out_layers[0], self.out_layers[3]
         g1 = ops.group_norm_nhwc(xt, gn1.weight, gn1.bias, gn1.eps, gn1.num_groups, silu=True, x2=x2t)
         h1 = F.conv2d(g1.permute(0, 3, 1, 2), conv1.weight, None, padding=1)
-        add = self.emb_layers(emb).type(h1.dtype) + conv1.bias
+        add = self._emb_plus_conv_bias(emb, conv1).type(h1.dtype)
         g2 = ops.group_norm_nhwc(h1.permute(0, 2, 3, 1).contiguous(), gn2.weight, gn2.bias, gn2.eps, gn2.num_groups,
                                  silu=True, add_nc=add)
         h2 = F.conv2d(g2.permute(0, 3, 1, 2), conv2.weight, None, padding=1).permute(0, 2, 3, 1).contiguous()
@@ -146,7 +169,7 @@ class ResBlock(TimestepBlock):
         if x2t is not None:
             if isinstance(self.skip_connection, nn.Identity) or self.skip_connection.kernel_size != (1, 1):
                 raise NotImplementedError("a concatenated ResBlock input needs the 1x1 skip convolution")
-            bias = bias + self.skip_connection.bias
+            bias = self._bias_sum(self, "_out_skip_bias", bias, self.skip_connection.bias)
             w1, w2 = self._split_skip_weight(c)
             if fuse:
                 out = ops.linear_residual(xt.reshape(rows, c), w1, bias, h2.reshape(rows, self.out_channels))
@@ -158,7 +181,7 @@ class ResBlock(TimestepBlock):
         elif isinstance(self.skip_connection, nn.Identity):
             skip = xt
         elif self.skip_connection.kernel_size == (1, 1):
-            bias = bias + self.skip_connection.bias
+            bias = self._bias_sum(self, "_out_skip_bias", bias, self.skip_connection.bias)
             w = self.skip_connection.weight.reshape(self.out_channels, c)
             if fuse and w.is_contiguous():
                 out = ops.linear_residual(xt.reshape(rows, c), w, bias, h2.reshape(rows, self.out_channels))
@@ -295,6 +318,7 @@ class UNetModel(nn.Module):
             self.to(memory_format=torch.channels_last)       # conv weights NHWC once; keys/values unchanged
             self._weights_channels_last = True
         emb = self.time_embed(timestep_embedding(timesteps, self.model_channels).to(dt))
+        emb._vf_silu = F.silu(emb)              # every ResBlock's emb_layers starts with the same SiLU(emb): once, not 22 times
         context = context.to(dt)
         h = x.to(dt).contiguous(memory_format=torch.channels_last)
         hs = []
