@@ -382,6 +382,22 @@ def test_attention_streamed_arrangement_env_knob():
     assert res.returncode == 0 and "ATTN_AB_OK" in res.stdout, res.stdout[-3000:] + res.stderr[-2000:]
 
 
+@pytest.mark.parametrize("knob", [{"VF_ATTN_PP": "1"}, {"VF_ATTN_PP": "3"}, {"VF_ATTN_EARLY": "1"}, {"VF_ATTN_EARLY": "2"}])
+def test_attention_experimental_arrangements_env_knobs(knob):
+    """Round-2 experiments kept as opt-ins (read once per process, so each runs in a fresh interpreter): the round-robin
+    arrangement (csrc/vf_attn_pp.cu: one CTA per SM, three query tiles, softmax warps taking turns on the XU / unordered)
+    and the early barrier probes of the default kernel.  Same cases as the default: ragged sizes, second K/V segment,
+    strided views, score jumps."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, **knob)
+    res = subprocess.run([sys.executable, os.path.join(root, "benchmarks", "attn_ab.py"), "--quick", "--no-timing"],
+                         capture_output=True, text=True, env=env, timeout=600, cwd=root)
+    assert res.returncode == 0 and "ATTN_AB_OK" in res.stdout, res.stdout[-3000:] + res.stderr[-2000:]
+
+
 def test_errors_are_loud():
     from vface_b200 import ops
     x = torch.zeros(1, 64, 44, device=_dev(), dtype=torch.bfloat16)

@@ -90,7 +90,14 @@ template <int kRegs> __device__ __forceinline__ void reg_inc() { asm volatile("s
 // as the softmax threads have loaded it into registers (s_free), so QK_{j+1} is issued while softmax_j is
 // still in its exponentials and the softmax warps never wait for the tensor pipe; PV_j follows when P_j is
 // complete (p_full) and releases P with its own commit (p_empty).  160 TMEM columns -> three CTAs per SM.
-template <int BN, int kTmemCols, int kMinBlocks, int kEmu, int kPMode, int kStages, bool kLagMax>
+// kEarly (split-P modes): the two barrier waits of a tile (s_full of the NEXT tile, p_empty of the previous one) are
+// probed with a non-blocking mbarrier.test_wait in the MIDDLE of the exponential section.  Both barriers complete
+// hundreds of cycles before the softmax warps ask (profiles/r1_attn_trace_completion.txt); what the blocking form
+// costs is the round trip of the probe itself through the instruction queue the MUFU stream of the other warps
+// keeps full (400 + 110 cycles of a 2150-cycle tile).  Issued early, that round trip runs under this warp's own
+// exponentials; the blocking wait remains as the fallback when a probe comes back negative.  kEarly = the element
+// index of the section at which the probes are issued (S_{j+1} completes ~60 % into the section, PV_{j-1} ~50 %).
+template <int BN, int kTmemCols, int kMinBlocks, int kEmu, int kPMode, int kStages, bool kLagMax, int kEarly = 0>
 __global__ void __launch_bounds__(kTcThreads, kMinBlocks)
 attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                const __grid_constant__ CUtensorMap map_v, const __grid_constant__ CUtensorMap map_k2,
@@ -319,6 +326,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     float m_ref = 0.0f, l = 0.0f;
     float lag_alpha = 1.0f, lag_m = 0.0f;          // kLagMax: rescale decided by the previous tile's row max
     bool lag_need = false;
+    bool s_probe = false, p_probe = false;         // kEarly: results of the probes issued inside the exponential section
     VF_TR_DECL;
 
     for (int j = 0; j < n_tiles; ++j) {
@@ -327,8 +335,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
       const int valid = min(BN, (seg2 ? P.n_kv2 : P.n_kv) - row0);
 
       // S_j complete; the commit also covers PV_{j-1}, so P/O are ours again.
-      if (P.spin) mbar_wait_spin(&bars.s_full, (uint32_t)j & 1);
-      else mbar_wait(&bars.s_full, (uint32_t)j & 1);
+      if (!(kEarly && kSplitP && j > 0 && s_probe)) {        // kEarly: already seen complete by the probe of tile j-1
+        if (P.spin) mbar_wait_spin(&bars.s_full, (uint32_t)j & 1);
+        else mbar_wait(&bars.s_full, (uint32_t)j & 1);
+      }
       tc_fence_after();
       VF_TR(j == 0 ? 0 : 1);            // 0: prologue until S_0, 1: s_full waits
       if (warp == 0) VF_EV(j, 0);       // s_full(j) passed
@@ -382,6 +392,11 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         }
 #pragma unroll
         for (int i = 0; i < BN; i += 4) {
+          if (kEarly && kSplitP && i == kEarly) {
+            // probes for the two waits that follow this section; their round trip runs under the remaining MUFUs
+            if (j + 1 < n_tiles) s_probe = mbar_test(&bars.s_full, (uint32_t)(j + 1) & 1);
+            if (j > 0) p_probe = mbar_test(&bars.p_empty, (uint32_t)(j - 1) & 1);
+          }
           const uint64_t xa = ffma2(pack2(__uint_as_float(sr[i + 0]), __uint_as_float(sr[i + 1])), c2, nm2);
           const uint64_t xb = ffma2(pack2(__uint_as_float(sr[i + 2]), __uint_as_float(sr[i + 3])), c2, nm2);
           if (with_max) {
@@ -460,8 +475,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
       VF_TR(4);                         // exponentials
       if (warp == 0) VF_EV(j, 2);       // exps done
       if (kSplitP && j > 0) {              // PV_{j-1} still reads P (and writes O) until its commit
-        if (P.spin) mbar_wait_spin(&bars.p_empty, (uint32_t)(j - 1) & 1);
-        else mbar_wait(&bars.p_empty, (uint32_t)(j - 1) & 1);
+        if (!(kEarly && p_probe)) {
+          if (P.spin) mbar_wait_spin(&bars.p_empty, (uint32_t)(j - 1) & 1);
+          else mbar_wait(&bars.p_empty, (uint32_t)(j - 1) & 1);
+        }
         tc_fence_after();
       }
       VF_TR(5);                         // p_empty wait
@@ -567,17 +584,17 @@ int attn_make_map(CUtensorMap* m, const void* base, int batch, int heads, int n,
   return 0;
 }
 
-template <int BN, int kTmemCols, int kMinBlocks, int kEmu, int kPMode = 0, int kStages = 2, bool kLagMax = false>
+template <int BN, int kTmemCols, int kMinBlocks, int kEmu, int kPMode = 0, int kStages = 2, bool kLagMax = false, int kEarly = 0>
 static int launch_tc(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const CUtensorMap& mk2,
                      const CUtensorMap& mv2, const AttnTcParams& P, int batch, cudaStream_t st) {
   const size_t smem = 1024 + (size_t)P.kb * (kBM * 128 + 2 * kStages * BN * 128);
   static bool attr = false;
   if (!attr) {
-    VF_CUDA_TRY(cudaFuncSetAttribute(attn_tc_kernel<BN, kTmemCols, kMinBlocks, kEmu, kPMode, kStages, kLagMax>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    VF_CUDA_TRY(cudaFuncSetAttribute(attn_tc_kernel<BN, kTmemCols, kMinBlocks, kEmu, kPMode, kStages, kLagMax, kEarly>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr = true;
   }
   dim3 grid((P.n_q + kBM - 1) / kBM, batch * P.heads);
-  attn_tc_kernel<BN, kTmemCols, kMinBlocks, kEmu, kPMode, kStages, kLagMax><<<grid, kTcThreads, smem, st>>>(mq, mk, mv, mk2, mv2, P);
+  attn_tc_kernel<BN, kTmemCols, kMinBlocks, kEmu, kPMode, kStages, kLagMax, kEarly><<<grid, kTcThreads, smem, st>>>(mq, mk, mv, mk2, mv2, P);
   return check_cuda(cudaGetLastError(), "attn_tc_kernel launch");
 }
 
@@ -645,6 +662,13 @@ int launch_attn_tc(const void* q, const void* k, const void* v, void* o, int bat
     const char* e = getenv("VF_ATTN_STREAM");
     stream_mode = e ? atoi(e) : 0;
   }
+  // VF_ATTN_PP: round-robin arrangement (vf_attn_pp.cu) for d_head <= 64 and at least 3 query tiles -- 1 / 2: one / two
+  // softmax warps of a scheduler in their exponentials at a time, 3: no ordering; 0 = the arrangements below.
+  static int pp_mode = -1;
+  if (pp_mode < 0) { const char* e = getenv("VF_ATTN_PP"); pp_mode = e ? atoi(e) : 0; }
+  if (pp_mode && P.d_pad <= 64 && n_q >= 3 * kBM)
+    return launch_attn_pp(q, k, v, o, batch, heads, n_q, n_kv, d, ld_q, ld_k, ld_v, ld_o, scale, k2, v2, n_kv2, ld_k2, ld_v2,
+                          pp_mode >= 3 ? 0 : pp_mode, st);
   if (d > 192 || (stream_mode && P.d_pad <= (stream_mode >= 2 ? 128 : 64)))
     return launch_attn_stream(q, k, v, o, batch, heads, n_q, n_kv, d, ld_q, ld_k, ld_v, ld_o, scale, k2, v2, n_kv2, ld_k2, ld_v2,
                               emu, st);
@@ -666,6 +690,24 @@ int launch_attn_tc(const void* q, const void* k, const void* v, void* o, int bat
       case 1: return launch_tc<48, 128, 4, 1, 2>(mq, mk, mv, mk2, mv2, P, batch, st);
       default: return launch_tc<48, 128, 4, 0, 2>(mq, mk, mv, mk2, mv2, P, batch, st);
     }
+  }
+  // VF_ATTN_EARLY: early barrier probes (kEarly) -- 1: at element 48 of 64, 2: the same with the lagged row max, 3: with 25 %
+  // of the exponentials on the FMA pipe, 4: both; 5 / 6: probes at element 32 / 56; 0 = the blocking waits.
+  static int early = -1;
+  if (early < 0) { const char* e = getenv("VF_ATTN_EARLY"); early = e ? atoi(e) : 0; }
+  if (P.d_pad <= 64 && split == 1 && early) {
+    switch (early) {
+      case 2: return launch_tc<64, 128, 3, 0, 1, 2, true, 48>(mq, mk, mv, mk2, mv2, P, batch, st);
+      case 3: return launch_tc<64, 128, 3, 1, 1, 2, false, 48>(mq, mk, mv, mk2, mv2, P, batch, st);
+      case 4: return launch_tc<64, 128, 3, 1, 1, 2, true, 48>(mq, mk, mv, mk2, mv2, P, batch, st);
+      case 5: return launch_tc<64, 128, 3, 0, 1, 2, false, 32>(mq, mk, mv, mk2, mv2, P, batch, st);
+      case 6: return launch_tc<64, 128, 3, 0, 1, 2, false, 56>(mq, mk, mv, mk2, mv2, P, batch, st);
+      default: return launch_tc<64, 128, 3, 0, 1, 2, false, 48>(mq, mk, mv, mk2, mv2, P, batch, st);
+    }
+  }
+  if (split && P.d_pad > 64 && P.d_pad <= 160 && early) {
+    if (early == 2 || early == 4) return launch_tc<64, 256, 2, 0, 2, 2, true, 48>(mq, mk, mv, mk2, mv2, P, batch, st);
+    return launch_tc<64, 256, 2, 0, 2, 2, false, 48>(mq, mk, mv, mk2, mv2, P, batch, st);
   }
   if (P.d_pad <= 64 && split == 2) return launch_tc<64, 128, 3, 0, 1, 3>(mq, mk, mv, mk2, mv2, P, batch, st);   // 3-stage K/V ring
   if (P.d_pad <= 64 && split) {

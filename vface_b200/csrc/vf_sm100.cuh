@@ -54,6 +54,18 @@ __device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
   } while (!ok);
 }
 
+// non-blocking probe: has the phase with this parity completed?  The result is a predicate ptxas keeps in flight until
+// its first use, so a probe issued early costs nothing but its issue slot.
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+
 // one lane of a converged warp (the surrounding control flow stays warp-uniform, so operands of the predicated
 // instruction can live in uniform registers)
 __device__ __forceinline__ bool elect_one() {
