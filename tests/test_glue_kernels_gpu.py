@@ -56,6 +56,36 @@ def test_group_norm_over_concatenation(dtype, tol, c1, c2):
     assert (got.float() - want).abs().max().item() < tol * max(1.0, want.abs().max().item() / 2.0)
 
 
+def test_group_norm_persistent_grid_and_counter_reuse():
+    """The one-launch GroupNorm (vf_norm.cu: gn_resident_kernel / gn_fused_kernel) hands (sample, slab) items to a
+    persistent grid through a ticket counter and synchronises the slabs of a sample through per-sample arrival counters
+    that the kernel itself re-arms.  Here: more work items than resident CTAs (96 samples), a ragged row count (short last
+    slab), a batch of one, and 45 back-to-back launches of alternating shapes -- a counter left dirty by one launch would
+    deadlock or corrupt the next -- every result against torch, and repeated launches bit-identical."""
+    from vface_b200 import ops
+    dtype = torch.bfloat16
+    shapes = [(96, 1000, 640), (1, 4096, 320), (7, 250, 1280), (96, 64, 1280), (33, 1024, 320)]
+    cases = []
+    for i, (n, hw, c) in enumerate(shapes):
+        x = _mk((n, hw, c), 40 + i, dtype, 1.3) - 0.2
+        w, b = _mk((c,), 50 + i, dtype), _mk((c,), 60 + i, dtype)
+        add = _mk((n, c), 70 + i, dtype) if i % 2 == 0 else None
+        xf = x.float() + (add.float()[:, None, :] if add is not None else 0.0)
+        want = F.silu(F.group_norm(xf.permute(0, 2, 1), 32, w.float(), b.float(), 1e-5).permute(0, 2, 1))
+        cases.append((x, w, b, add, want))
+    first = {}
+    for rep in range(9):
+        for i, (x, w, b, add, want) in enumerate(cases):
+            got = ops.group_norm_nhwc(x, w, b, 1e-5, 32, silu=True, add_nc=add)
+            if rep == 0:
+                first[i] = got
+                err = (got.float() - want).abs().max().item()
+                assert err < BF16_TOL * max(1.0, want.abs().max().item() / 2.0), (shapes[i], err)
+            else:
+                assert torch.equal(got, first[i]), (shapes[i], rep)
+    torch.cuda.synchronize()
+
+
 @pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-5), (torch.bfloat16, BF16_TOL)])
 @pytest.mark.parametrize("n,m,c", [(3, 4096, 320), (2, 1024, 640), (3, 253, 1280), (1, 7, 320), (2, 33, 64)])
 def test_layer_norm_forms(dtype, tol, n, m, c):

@@ -40,7 +40,10 @@ constexpr int kGemmBM = 128;          // rows per tile
 constexpr int kGemmBN = 128;          // OUTPUT columns per tile (256 accumulator columns: value + gate)
 constexpr int kGemmBK = 64;           // k-block: 64 bf16 = one 128-byte swizzled row
 constexpr int kGemmStages = 4;        // ring depth of the streaming kernel (A + W per stage)
-constexpr int kGemmStagesRes = 3;     // ring depth of the W-resident kernel (A only): the fourth stage's 16 KB hold the output staging
+#ifndef VF_GEMM_STAGES_RES
+#define VF_GEMM_STAGES_RES 3
+#endif
+constexpr int kGemmStagesRes = VF_GEMM_STAGES_RES;     // ring depth of the W-resident kernel (A only): the fourth stage's 16 KB hold the output staging
 constexpr uint32_t kATileBytes = kGemmBM * kGemmBK * 2;          // 16 KB
 constexpr uint32_t kBTileBytes = 2 * kGemmBN * kGemmBK * 2;      // 32 KB (value rows, then gate rows)
 constexpr uint32_t kStageBytes = kATileBytes + kBTileBytes;
