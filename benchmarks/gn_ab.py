@@ -34,8 +34,8 @@ SHAPES = [            # (n, hw, c1, c2, silu, add)
 CONFIGS = [
     ("two launches", dict(VF_GN_FUSED="0")),
     ("fused, L2 re-read, 160K", dict(VF_GN_FUSED="1", VF_GN_FUSED_CTAS="2", VF_GN_SLAB_KB="160")),
-    ("slab in smem", dict(VF_GN_FUSED="2")),
-    ("slab in smem, NO WAIT (wrong)", dict(VF_GN_FUSED="2", VF_GN_DEBUG_NOWAIT="1")),
+    ("slab in smem, fewest slabs", dict(VF_GN_FUSED="2", VF_GN_RES_QUANT="0")),
+    ("slab in smem, wave plan", dict(VF_GN_FUSED="2", VF_GN_RES_QUANT="1")),
 ]
 
 

@@ -1065,17 +1065,34 @@ gn_resident_kernel(const GnParams P, const int tpr, const int rpb, const int set
 }
 
 // slab plan: the largest slab (a multiple of rpb rows) within `budget` bytes; 0 slabs = does not fit the scheme
-static void gnr_plan(int hw, int c, int esize, int rpb, size_t budget, int* slabs, int* rows_per_slab) {
+static void gnr_plan(int n, int hw, int c, int esize, int rpb, size_t budget, int* slabs, int* rows_per_slab) {
   long long rows = (long long)(budget / ((size_t)c * esize));
   rows = rows / rpb * rpb;
   if (rows > hw) rows = (hw + rpb - 1) / rpb * rpb;
   if (rows < rpb) { *slabs = 0; *rows_per_slab = 0; return; }
-  int s = (int)((hw + rows - 1) / rows);
-  // even the slabs out (the last one would otherwise be a sliver)
-  rows = ((hw + s - 1) / s + rpb - 1) / rpb * rpb;
-  s = (int)((hw + rows - 1) / rows);
-  *slabs = s > kGnrMaxSlabs ? 0 : s;
-  *rows_per_slab = (int)rows;
+  const int s_min = (int)((hw + rows - 1) / rows);
+  // Default: the fewest slabs the budget allows.  VF_GN_RES_QUANT=1 searches a few more slab counts for the least
+  // (rounds over 2 CTAs per SM) x (bytes per item + a synchronisation chain worth ~32 KB) -- with 96 samples of 7 slabs the
+  // items make 2.27 rounds, three for the work of 2.27.  Measured equal or slightly slower (0.139 vs 0.132 ms at 96 x 4096 x
+  // 320, profiles/r2_gn_ab.txt): tickets already balance the tail and the chain, not the rounds, bounds the kernel.
+  static int quant = -1;
+  if (quant < 0) { const char* e_ = getenv("VF_GN_RES_QUANT"); quant = e_ ? atoi(e_) : 0; }
+  const long long ctas = 2LL * num_sms();
+  int best_s = 0;
+  long long best_rows = 0, best_cost = -1;
+  for (int s = s_min; s <= (quant ? s_min + 12 : s_min) && s <= kGnrMaxSlabs; ++s) {
+    long long r = ((hw + s - 1) / s + rpb - 1) / rpb * rpb;       // even slabs, a whole number of row lanes
+    if (r < rpb || r * (long long)c * esize > (long long)budget) continue;
+    const int s_eff = (int)((hw + r - 1) / r);
+    const long long items = (long long)n * s_eff;
+    const long long rounds = (items + ctas - 1) / ctas;
+    // an item costs its bytes plus a synchronisation chain worth ~32 KB of streaming (three CTAs per SM with 64 KB slabs
+    // measured 14 % slower than two with 100 KB); ties go to fewer slabs
+    const long long cost = rounds * (r * (long long)c * esize + 32768) * 256 + s_eff;
+    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_s = s_eff; best_rows = r; }
+  }
+  *slabs = best_s;
+  *rows_per_slab = (int)best_rows;
 }
 
 // Two CTAs per SM, ~100 KB slabs (three with ~64 KB slabs measured slower: 0.152 vs 0.135 ms at 96 x 4096 x 320 -- the
@@ -1528,7 +1545,7 @@ extern "C" int vf_group_norm_nhwc_cat(const void* x, int c1, const void* x2, int
         const int rpb_r = mt / tpr;
         const int threads_r = (tpr * rpb_r + 31) / 32 * 32;
         const size_t budget = gnr_smem_per_cta() - kGnrHeaderBytes - kGnrMaxThreads * sizeof(float4);
-        gnr_plan(hw, c, dtype == VF_F32 ? 4 : 2, rpb_r, budget, &P.slabs, &P.rows_per_slab);
+        gnr_plan(n, hw, c, dtype == VF_F32 ? 4 : 2, rpb_r, budget, &P.slabs, &P.rows_per_slab);
         if (P.slabs > 0)
           return dtype == VF_F32 ? gn_resident_launch<float>(P, tpr, rpb_r, threads_r, st)
                                  : gn_resident_launch<__nv_bfloat16>(P, tpr, rpb_r, threads_r, st);
