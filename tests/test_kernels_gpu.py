@@ -382,7 +382,8 @@ def test_attention_streamed_arrangement_env_knob():
     assert res.returncode == 0 and "ATTN_AB_OK" in res.stdout, res.stdout[-3000:] + res.stderr[-2000:]
 
 
-@pytest.mark.parametrize("knob", [{"VF_ATTN_PP": "1"}, {"VF_ATTN_PP": "3"}, {"VF_ATTN_EARLY": "1"}, {"VF_ATTN_EARLY": "2"}])
+@pytest.mark.parametrize("knob", [{"VF_ATTN_PP": "1"}, {"VF_ATTN_PP": "3"}, {"VF_ATTN_EARLY": "1"}, {"VF_ATTN_EARLY": "2"},
+                                  {"VF_ATTN_EARLY": "7"}])
 def test_attention_experimental_arrangements_env_knobs(knob):
     """Round-2 experiments kept as opt-ins (read once per process, so each runs in a fresh interpreter): the round-robin
     arrangement (csrc/vf_attn_pp.cu: one CTA per SM, three query tiles, softmax warps taking turns on the XU / unordered)

@@ -53,6 +53,7 @@ struct AttnTcParams {
   float scale_log2;                            // scale * log2(e)
   int spin;                                    // tuning knob: poll instead of suspending on the softmax-side barriers
   int issue;                                   // MMA issue order in the split-P modes (see the issuer section)
+  int one;                                     // 1: trip count of the single-pass loop of the kFence variant
 };
 
 constexpr int kMaxStages = 4;
@@ -97,7 +98,7 @@ template <int kRegs> __device__ __forceinline__ void reg_inc() { asm volatile("s
 // keeps full (400 + 110 cycles of a 2150-cycle tile).  Issued early, that round trip runs under this warp's own
 // exponentials; the blocking wait remains as the fallback when a probe comes back negative.  kEarly = the element
 // index of the section at which the probes are issued (S_{j+1} completes ~60 % into the section, PV_{j-1} ~50 %).
-template <int BN, int kTmemCols, int kMinBlocks, int kEmu, int kPMode, int kStages, bool kLagMax, int kEarly = 0>
+template <int BN, int kTmemCols, int kMinBlocks, int kEmu, int kPMode, int kStages, bool kLagMax, int kEarly = 0, bool kFence = false>
 __global__ void __launch_bounds__(kTcThreads, kMinBlocks)
 attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                const __grid_constant__ CUtensorMap map_v, const __grid_constant__ CUtensorMap map_k2,
@@ -437,7 +438,38 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
           need = true;
         }
         VF_TR(3);                         // row max, rescale decision
-        exps(false);
+        if (kFence) {
+          // kFence: the 64 MUFU.EX2 as one bare stream, their consumers (row sums, bf16 packing) behind a single-pass loop
+          // whose trip count ptxas does not know (a basic-block boundary).  Inside one block ptxas threads the consumers
+          // between the MUFUs, where each stalls the in-order warp until its operands are back from the XU queue
+          // (experiments/mufu_rate.cu: one warp per scheduler sustains 15.7 MUFU/clk/SM bare, 10.6 with them threaded in).
+          const uint64_t nm2 = pack2(-m_ref, -m_ref);
+          float ex[BN];
+#pragma unroll
+          for (int i = 0; i < BN; i += 2) {
+            const uint64_t x2 = ffma2(pack2(__uint_as_float(sr[i + 0]), __uint_as_float(sr[i + 1])), c2, nm2);
+            unpack2(x2, ex[i], ex[i + 1]);
+          }
+#pragma unroll
+          for (int i = 0; i < BN; ++i) asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex[i]) : "f"(ex[i]));
+          acc_a = 0ull; acc_b = 0ull;
+#pragma unroll
+          for (int i = 0; i < BN / 2; ++i) pk[i] = 0u;
+#pragma unroll 1
+          for (int once = 0; once < P.one; ++once) __syncwarp();       // a block of its own between the stream and its consumers
+#pragma unroll 1
+          for (int once = 0; once < P.one; ++once) {
+#pragma unroll
+            for (int i = 0; i < BN; i += 4) {
+              acc_a = fadd2(acc_a, pack2(ex[i + 0], ex[i + 1]));
+              acc_b = fadd2(acc_b, pack2(ex[i + 2], ex[i + 3]));
+              pk[i / 2 + 0] = pack_bf16(ex[i + 0], ex[i + 1]);
+              pk[i / 2 + 1] = pack_bf16(ex[i + 2], ex[i + 3]);
+            }
+          }
+        } else {
+          exps(false);
+        }
       } else {
         // Lagged reference: the exponentials of tile j use the reference decided from tiles < j (lag_alpha /
         // lag_need carry the O, l rescale that decision implies), while this tile's row max is computed in the
@@ -584,17 +616,17 @@ int attn_make_map(CUtensorMap* m, const void* base, int batch, int heads, int n,
   return 0;
 }
 
-template <int BN, int kTmemCols, int kMinBlocks, int kEmu, int kPMode = 0, int kStages = 2, bool kLagMax = false, int kEarly = 0>
+template <int BN, int kTmemCols, int kMinBlocks, int kEmu, int kPMode = 0, int kStages = 2, bool kLagMax = false, int kEarly = 0, bool kFence = false>
 static int launch_tc(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const CUtensorMap& mk2,
                      const CUtensorMap& mv2, const AttnTcParams& P, int batch, cudaStream_t st) {
   const size_t smem = 1024 + (size_t)P.kb * (kBM * 128 + 2 * kStages * BN * 128);
   static bool attr = false;
   if (!attr) {
-    VF_CUDA_TRY(cudaFuncSetAttribute(attn_tc_kernel<BN, kTmemCols, kMinBlocks, kEmu, kPMode, kStages, kLagMax, kEarly>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    VF_CUDA_TRY(cudaFuncSetAttribute(attn_tc_kernel<BN, kTmemCols, kMinBlocks, kEmu, kPMode, kStages, kLagMax, kEarly, kFence>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr = true;
   }
   dim3 grid((P.n_q + kBM - 1) / kBM, batch * P.heads);
-  attn_tc_kernel<BN, kTmemCols, kMinBlocks, kEmu, kPMode, kStages, kLagMax, kEarly><<<grid, kTcThreads, smem, st>>>(mq, mk, mv, mk2, mv2, P);
+  attn_tc_kernel<BN, kTmemCols, kMinBlocks, kEmu, kPMode, kStages, kLagMax, kEarly, kFence><<<grid, kTcThreads, smem, st>>>(mq, mk, mv, mk2, mv2, P);
   return check_cuda(cudaGetLastError(), "attn_tc_kernel launch");
 }
 
@@ -630,6 +662,7 @@ int launch_attn_tc(const void* q, const void* k, const void* v, void* o, int bat
     static int issue = -1;
     if (issue < 0) { const char* e = getenv("VF_ATTN_ISSUE"); issue = e ? atoi(e) : 1; }
     P.issue = issue;
+    P.one = 1;
   }
   static int emu = -1;      // tuning knob: VF_ATTN_EMU = 0..3 pairs of every 4 on the FMA pipe
   if (emu < 0) {
@@ -692,7 +725,8 @@ int launch_attn_tc(const void* q, const void* k, const void* v, void* o, int bat
     }
   }
   // VF_ATTN_EARLY: early barrier probes (kEarly) -- 1: at element 48 of 64, 2: the same with the lagged row max, 3: with 25 %
-  // of the exponentials on the FMA pipe, 4: both; 5 / 6: probes at element 32 / 56; 0 = the blocking waits.
+  // of the exponentials on the FMA pipe, 4: both; 5 / 6: probes at element 32 / 56; 7: no probes, the exponentials as one bare
+  // MUFU stream with their consumers fenced off (kFence); 0 = the blocking waits.
   static int early = -1;
   if (early < 0) { const char* e = getenv("VF_ATTN_EARLY"); early = e ? atoi(e) : 0; }
   if (P.d_pad <= 64 && split == 1 && early) {
@@ -702,6 +736,7 @@ int launch_attn_tc(const void* q, const void* k, const void* v, void* o, int bat
       case 4: return launch_tc<64, 128, 3, 1, 1, 2, true, 48>(mq, mk, mv, mk2, mv2, P, batch, st);
       case 5: return launch_tc<64, 128, 3, 0, 1, 2, false, 32>(mq, mk, mv, mk2, mv2, P, batch, st);
       case 6: return launch_tc<64, 128, 3, 0, 1, 2, false, 56>(mq, mk, mv, mk2, mv2, P, batch, st);
+      case 7: return launch_tc<64, 128, 3, 0, 1, 2, false, 0, true>(mq, mk, mv, mk2, mv2, P, batch, st);     // bare MUFU stream
       default: return launch_tc<64, 128, 3, 0, 1, 2, false, 48>(mq, mk, mv, mk2, mv2, P, batch, st);
     }
   }
