@@ -56,6 +56,27 @@ def test_group_norm_over_concatenation(dtype, tol, c1, c2):
     assert (got.float() - want).abs().max().item() < tol * max(1.0, want.abs().max().item() / 2.0)
 
 
+def test_group_norm_full_size_properties():
+    """Size-independent properties at the shape of a 32-frame step (96 x 64 x 64 x 320): the output does not change under a
+    positive rescaling plus shift of a whole sample (eps aside), every (sample, group) of the normalised tensor has mean
+    beta-weighted 0 and variance 1 when gamma = 1, beta = 0, and the per-sample additive vector equals adding it first."""
+    from vface_b200 import ops
+    dtype = torch.float32
+    n, hw, c = 96, 4096, 320
+    x = _mk((n, hw, c), 91, dtype, 1.7) + 0.4
+    ones, zeros = torch.ones(c, device=_dev()), torch.zeros(c, device=_dev())
+    y = ops.group_norm_nhwc(x, ones, zeros, 1e-6, 32)
+    yg = y.view(n, hw, 32, c // 32)
+    assert yg.mean(dim=(1, 3)).abs().max().item() < 1e-4
+    assert (yg.var(dim=(1, 3), unbiased=False) - 1.0).abs().max().item() < 1e-3
+    y2 = ops.group_norm_nhwc(3.0 * x + 5.0, ones, zeros, 1e-6, 32)
+    assert (y2 - y).abs().max().item() < 2e-4
+    add = _mk((n, c), 92, dtype)
+    ya = ops.group_norm_nhwc(x, ones, zeros, 1e-6, 32, add_nc=add)
+    yb = ops.group_norm_nhwc(x + add[:, None, :], ones, zeros, 1e-6, 32)
+    assert (ya - yb).abs().max().item() < 2e-4
+
+
 def test_group_norm_persistent_grid_and_counter_reuse():
     """The one-launch GroupNorm (vf_norm.cu: gn_resident_kernel / gn_fused_kernel) hands (sample, slab) items to a
     persistent grid through a ticket counter and synchronises the slabs of a sample through per-sample arrival counters

@@ -369,6 +369,30 @@ def test_attention_wide_head_vs_oracle(b, n_q, n_kv, heads, d):
     assert err < BF16_TOL, err
 
 
+def test_attention_full_size_properties():
+    """Size-independent properties at BASELINE.json's configs[1] shape (96 frame-branches x 4096 tokens, 8 heads x d40), where no
+    CPU oracle finishes: softmax rows sum to one (V = 1 gives 1), keys may be permuted together with their values, the output
+    is linear in V, and a second K/V segment equals the concatenation."""
+    from vface_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(5)
+    b, n, h, d = 96, 4096, 8, 40
+    mk = lambda *s: torch.randn(*s, device=_dev(), generator=g).bfloat16()
+    q, k, v = mk(b, n, h * d), mk(b, n, h * d), mk(b, n, h * d)
+    ones = torch.ones_like(v)
+    o1 = ops.attention(q, k, ones, h).float()
+    assert (o1 - 1.0).abs().max().item() < 8e-3                      # the bf16 rounding of P leaves the row sum within 2^-8
+    o = ops.attention(q, k, v, h).float()
+    perm = torch.randperm(n, device=_dev(), generator=g)
+    op = ops.attention(q, k[:, perm].contiguous(), v[:, perm].contiguous(), h).float()
+    assert (op - o).abs().max().item() < BF16_TOL
+    o2 = ops.attention(q, k, (2 * v.float()).bfloat16(), h).float()  # doubling is exact in bf16
+    assert (o2 - 2 * o).abs().max().item() < BF16_TOL
+    half = n // 2
+    oc = ops.attention(q, k[:, :half].contiguous(), v[:, :half].contiguous(), h,
+                       k2=k[:, half:].contiguous(), v2=v[:, half:].contiguous()).float()
+    assert (oc - o).abs().max().item() < BF16_TOL
+
+
 def test_attention_streamed_arrangement_env_knob():
     """The streamed-softmax arrangement (csrc/vf_attn_stream.cu) for d_head <= 64 is an opt-in (VF_ATTN_STREAM=1, read once
     per process): run it in a fresh interpreter against the fp32 kernel, incl. the exact-path and deferred-rescale cases."""

@@ -336,11 +336,13 @@ static void gn_plan(int n, int hw, int* slabs, int* rows_per_slab) {
 //     CTA that is already running (it only waits on tickets lower than or next to its own);
 //   * statistics stay bit-reproducible: per-slab partials in a fixed order, per-sample totals in a fixed order;
 //   * the counters clean up after themselves (the last CTA to leave a sample / the grid resets them), live in
-//     module-global memory and are rotated over kGnSyncSets launches.
+//     module-global memory and are rotated over kGnSyncSets launches.  Launches in stream order (the sampler's single
+//     compute stream, CUDA-graph replays included) never share a live set; GroupNorm launches that run CONCURRENTLY on
+//     different streams are only safe while fewer than kGnSyncSets of them are in flight (VF_GN_FUSED=0 has no such state).
 //   * the block is tpr x rpb threads (chunks per row x rows per trip, rounded up to a warp) so no lane idles at
 //     c = 1280 / 1920 / 2560, and every thread keeps kGnfUnroll 16-byte loads in flight.
 constexpr int kGnfMaxThreads = 320;
-constexpr int kGnSyncSets = 4;
+constexpr int kGnSyncSets = 8;
 constexpr int kGnfMaxN = 4096;
 __device__ unsigned int g_gn_sync[kGnSyncSets][2 + 2 * kGnfMaxN];     // ticket, finished, then (arrived, departed) per sample
 
