@@ -462,6 +462,22 @@ def test_linear_geglu_vs_reference_form(rows, k, n):
     assert (got_nb - val * torch.nn.functional.gelu(gate)).abs().max().item() < BF16_TOL * max(1.0, want.abs().max().item() / 4)
 
 
+@pytest.mark.parametrize("knob", [{"VF_GEMM_PAIR": "1"}, {"VF_GEMM_PAIR": "1", "VF_GEMM_GELU": "0"}, {"VF_GEMM_GELU": "0"}])
+def test_linear_geglu_cta_pair_and_gelu_knobs(knob):
+    """The CTA-pair kernel (csrc/vf_gemm2.cu: tcgen05.mma.cta_group::2, both CTAs' TMA loads signalling the leader's
+    barriers, multicast commits, remote arrivals) and the A&S-erf epilogue are opt-ins read once per process: fresh
+    interpreter, the 64x64-level shape of a 32-frame step (the pair kernel needs >= 28 row blocks of 256 per n-block),
+    ragged rows and k = 256, against an fp32 reference on the GPU."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, **knob)
+    res = subprocess.run([sys.executable, os.path.join(root, "benchmarks", "geglu_pair_check.py")],
+                         capture_output=True, text=True, env=env, timeout=600, cwd=root)
+    assert res.returncode == 0 and "PAIR_CHECK_OK" in res.stdout, res.stdout[-3000:] + res.stderr[-2000:]
+
+
 def test_linear_geglu_matches_unfused_module_path():
     """The GEGLU module gives the same result (to bf16 round-off) through the fused kernel and through library
     GEMM + vf_geglu (VF_FUSED_GEGLU=0)."""

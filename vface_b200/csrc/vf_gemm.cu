@@ -146,7 +146,27 @@ __device__ __forceinline__ float2 geglu_pair(float2 v, float2 g) {
   return __fmul2_rn(v, __ffma2_rn(hg, sg, hg));
 }
 
-template <bool kWResident, int kEpiGroups>      // kEpiGroups: 1 = four epilogue warps (4-7), 2 = eight (4-11)
+// The same product with ONE transcendental per element: Phi(g) = 1/2 + 1/2 tanh(u), u = g (c1 + c3 g^2 + c5 g^4) fitted to
+// atanh(erf(g / sqrt 2)) (max |error| of g Phi(g) 3e-5 in exact arithmetic, g^2 clamped at 49 so that the quintic cannot
+// turn over: beyond |g| = 7 the tanh is saturated either way), evaluated with tanh.approx.f32 (|rel err| < 2^-10.9, the
+// instruction the GroupNorm's SiLU already uses): ~2.5e-4 |g| absolute, an eighth of the bf16 rounding of the output.
+// The A&S form costs two MUFU (rcp, ex2) and ~12 issue slots per element, and at k = 320 the EPILOGUE bounds the kernel
+// (a CTA pair with an eight-stage A ring runs at the same 0.55 ms as the single CTA with three: vf_gemm2.cu); this one
+// costs one MUFU and ~6 slots.  VF_GEMM_GELU=0 selects the A&S form.
+__device__ __forceinline__ float2 geglu_pair_tanh(float2 v, float2 g) {
+  const float2 g2 = __fmul2_rn(g, g);
+  const float2 y2 = make_float2(fminf(g2.x, 49.0f), fminf(g2.y, 49.0f));
+  float2 p = __ffma2_rn(y2, splat2(-0.0003587323612f), splat2(0.0370503451f));
+  p = __ffma2_rn(p, y2, splat2(0.7974584708f));
+  const float2 u = __fmul2_rn(g, p);
+  float2 t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t.x) : "f"(u.x));
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t.y) : "f"(u.y));
+  const float2 hg = __fmul2_rn(g, splat2(0.5f));
+  return __fmul2_rn(v, __ffma2_rn(hg, t, hg));               // v * (g/2 + g/2 tanh u)
+}
+
+template <bool kWResident, int kEpiGroups, int kGelu = 1>      // kEpiGroups: 1 = four epilogue warps (4-7), 2 = eight (4-11); kGelu: 0 A&S erf, 1 single tanh
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_geglu_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
                   const __grid_constant__ CUtensorMap map_o, const GemmGegluParams P) {
@@ -306,7 +326,8 @@ gemm_geglu_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
           const float2 vb = __fadd2_rn(make_float2(__uint_as_float(v[i + 2]), __uint_as_float(v[i + 3])), make_float2(bv.z, bv.w));
           const float2 ga = __fadd2_rn(make_float2(__uint_as_float(g[i]), __uint_as_float(g[i + 1])), make_float2(bg.x, bg.y));
           const float2 gb = __fadd2_rn(make_float2(__uint_as_float(g[i + 2]), __uint_as_float(g[i + 3])), make_float2(bg.z, bg.w));
-          const float2 oa = geglu_pair(va, ga), ob = geglu_pair(vb, gb);
+          const float2 oa = kGelu ? geglu_pair_tanh(va, ga) : geglu_pair(va, ga);
+          const float2 ob = kGelu ? geglu_pair_tanh(vb, gb) : geglu_pair(vb, gb);
           pk[i / 2] = pack_bf16(oa.x, oa.y);
           pk[i / 2 + 1] = pack_bf16(ob.x, ob.y);
         }
@@ -393,6 +414,10 @@ static int make_map_out(CUtensorMap* m, void* base, long long rows, int n, const
   return 0;
 }
 
+// CTA-pair kernel of vf_gemm2.cu (k <= 320): -1 = shape not eligible
+int launch_gemm_geglu_pair(const void* x, const void* w, const void* bias, void* out, long long rows, int k, int n,
+                           long long ld_x, cudaStream_t st);
+
 }  // namespace vf
 
 extern "C" int vf_linear_geglu(const void* x, const void* w, const void* bias, void* out,
@@ -407,6 +432,13 @@ extern "C" int vf_linear_geglu(const void* x, const void* w, const void* bias, v
   const void* ptrs[3] = {x, w, out};
   for (const void* p : ptrs)
     if (reinterpret_cast<uintptr_t>(p) & 15) return fail("vf_linear_geglu: pointers must be 16-byte aligned");
+  // VF_GEMM_PAIR=1: CTA pairs (tcgen05.mma.cta_group::2, vf_gemm2.cu) where the weight tile would otherwise be resident
+  static int pair_knob = -1;
+  if (pair_knob < 0) { const char* e = getenv("VF_GEMM_PAIR"); pair_knob = e ? atoi(e) : 0; }
+  if (pair_knob && k <= 320 && k % 64 == 0) {
+    const int rc = launch_gemm_geglu_pair(x, w, bias, out, rows, k, n, ld_x, (cudaStream_t)stream);
+    if (rc >= 0) return rc;
+  }
   CUtensorMap ma, mw, mo;
   if (int rc = make_map_2d(&ma, x, rows, k, ld_x, "vf_linear_geglu")) return rc;
   if (int rc = make_map_2d(&mw, w, 2LL * n, k, k, "vf_linear_geglu")) return rc;
@@ -425,6 +457,8 @@ extern "C" int vf_linear_geglu(const void* x, const void* w, const void* bias, v
   static int pf_knob = -1;
   if (pf_knob < 0) { const char* e = getenv("VF_GEMM_PREFETCH"); pf_knob = e ? atoi(e) : 1; }
   P.prefetch = pf_knob;
+  static int gelu_knob = -1;       // VF_GEMM_GELU: 1 (default) single-tanh GELU in the epilogue, 0 the A&S erf form
+  if (gelu_knob < 0) { const char* e = getenv("VF_GEMM_GELU"); gelu_knob = e ? atoi(e) : 1; }
   static int epi_res = -1;         // VF_GEMM_EPI_RES: epilogue warp groups of the W-resident kernel (1 or 2)
   if (epi_res < 0) { const char* e = getenv("VF_GEMM_EPI_RES"); epi_res = e ? atoi(e) : 2; if (epi_res != 1) epi_res = 2; }
   const size_t smem_res = 1008 + (size_t)P.k_blocks * kBTileBytes + (size_t)kGemmStagesRes * kATileBytes + 2 * kStageOutBytes +
@@ -433,24 +467,28 @@ extern "C" int vf_linear_geglu(const void* x, const void* w, const void* bias, v
   if (resident) {
     static size_t attr_r = 0;
     if (smem_res > attr_r) {
-      VF_CUDA_TRY(cudaFuncSetAttribute(gemm_geglu_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_res));
-      VF_CUDA_TRY(cudaFuncSetAttribute(gemm_geglu_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_res));
+      VF_CUDA_TRY(cudaFuncSetAttribute(gemm_geglu_kernel<true, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_res));
+      VF_CUDA_TRY(cudaFuncSetAttribute(gemm_geglu_kernel<true, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_res));
+      VF_CUDA_TRY(cudaFuncSetAttribute(gemm_geglu_kernel<true, 2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_res));
       attr_r = smem_res;
     }
     const int groups = num_sms() / P.n_blocks;
-    if (epi_res == 1) gemm_geglu_kernel<true, 1><<<groups * P.n_blocks, 256, smem_res, (cudaStream_t)stream>>>(ma, mw, mo, P);
-    else gemm_geglu_kernel<true, 2><<<groups * P.n_blocks, kGemmThreads, smem_res, (cudaStream_t)stream>>>(ma, mw, mo, P);
+    if (epi_res == 1) gemm_geglu_kernel<true, 1, 1><<<groups * P.n_blocks, 256, smem_res, (cudaStream_t)stream>>>(ma, mw, mo, P);
+    else if (gelu_knob) gemm_geglu_kernel<true, 2, 1><<<groups * P.n_blocks, kGemmThreads, smem_res, (cudaStream_t)stream>>>(ma, mw, mo, P);
+    else gemm_geglu_kernel<true, 2, 0><<<groups * P.n_blocks, kGemmThreads, smem_res, (cudaStream_t)stream>>>(ma, mw, mo, P);
     return check_cuda(cudaGetLastError(), "gemm_geglu_kernel<resident W> launch");
   }
   const size_t smem = 1008 + (size_t)kGemmStages * kStageBytes + 2 * kStageOutBytes + kTail;
   static_assert(1008 + (size_t)kGemmStages * kStageBytes + 2 * kStageOutBytes + kTail <= 232448, "streaming kernel shared memory");
   static bool attr = false;
   if (!attr) {
-    VF_CUDA_TRY(cudaFuncSetAttribute(gemm_geglu_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    VF_CUDA_TRY(cudaFuncSetAttribute(gemm_geglu_kernel<false, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    VF_CUDA_TRY(cudaFuncSetAttribute(gemm_geglu_kernel<false, 2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = true;
   }
   long long grid = (long long)P.m_blocks * P.n_blocks;
   if (grid > num_sms()) grid = num_sms();
-  gemm_geglu_kernel<false, 2><<<(int)grid, kGemmThreads, smem, (cudaStream_t)stream>>>(ma, mw, mo, P);
+  if (gelu_knob) gemm_geglu_kernel<false, 2, 1><<<(int)grid, kGemmThreads, smem, (cudaStream_t)stream>>>(ma, mw, mo, P);
+  else gemm_geglu_kernel<false, 2, 0><<<(int)grid, kGemmThreads, smem, (cudaStream_t)stream>>>(ma, mw, mo, P);
   return check_cuda(cudaGetLastError(), "gemm_geglu_kernel launch");
 }
