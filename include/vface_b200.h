@@ -33,7 +33,7 @@ extern "C" {
 #define VF_F32 0
 #define VF_BF16 1
 
-#define VF_ABI_VERSION 8
+#define VF_ABI_VERSION 9
 
 /* ABI version of the loaded library (== VF_ABI_VERSION). */
 int vf_abi_version(void);
@@ -232,6 +232,28 @@ int vf_linear_residual(const void* x, const void* w, const void* bias, const voi
 int vf_linear_residual_batched(const void* x, const void* w, const void* bias, const void* residual, void* out,
                                int batch, long long rows, int k, int n, long long ld_x, long long ld_res, long long ld_out,
                                void* workspace, long long workspace_bytes, int dtype, void* stream);
+
+/*
+ * Projection of the 64x64 transformer level as ONE tcgen05 kernel, with the LayerNorm in front of it, the bias (one row,
+ * or one row per sample) and the residual add behind it folded in:
+ *   out[r, 0:n] = LN(x[r, 0:k]) . W^T + bias[r / rows_per_bias, 0:n] + residual[r, 0:n]
+ * Replaces `self.attn1(self.norm1(x))`'s norm + to_q / to_k / to_v (ldm/modules/attention.py:239, :172-174; the hooked
+ * closure's projections, ldm/models/pnp_utils.py:106,127-128), to_out + the adds of attention.py:239-241 (:176,:221;
+ * pnp_utils.py:287), and the 1x1 convolutions proj_in / proj_out (+ x_in) of SpatialTransformer (attention.py:261-288).
+ *   w          (n, k) bf16 row-major.  LayerNorm form: the caller passes W o gamma (gamma folded into the columns, rounded
+ *              to bf16) and ln_colsum[j] = sum_k float(w[j, k]) (fp32, n entries); LN's beta enters through the bias
+ *              (beta . W^T); mean and rstd are computed in the kernel from the raw rows (eps = ln_eps).
+ *              ln_colsum NULL: no normalisation.
+ *   bias       fp32, (n) with rows_per_bias = 0, or (rows / rows_per_bias, n) with rows_per_bias % 128 == 0; may be NULL.
+ *   residual   bf16 (rows, n), row stride ld_res, or NULL (not together with ln_colsum).  out (rows, n) bf16, row stride
+ *              ld_out; no aliasing.
+ * k a multiple of 64 up to 320, n a multiple of 160 (vf_linear_proj_supported), bf16 only; other shapes and fp32 stay on
+ * the library GEMM (vf_linear_residual).
+ */
+int vf_linear_proj_supported(long long rows, int k, int n);
+int vf_linear_proj(const void* x, const void* w, const float* bias, long long rows_per_bias, const void* residual,
+                   const float* ln_colsum, float ln_eps, void* out, long long rows, int k, int n, long long ld_x,
+                   long long ld_res, long long ld_out, int dtype, void* stream);
 
 #ifdef __cplusplus
 }

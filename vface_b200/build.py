@@ -18,7 +18,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ_DIR = os.path.join(HERE, "csrc", "build")
 LIB_PATH = os.path.join(HERE, "libvface_b200.so")
 
-SOURCES = ["vf_capi.cu", "vf_ddim.cu", "vf_flow_warp.cu", "vf_fsai.cu", "vf_attn.cu", "vf_attn_f32.cu", "vf_attn_tc.cu", "vf_attn_stream.cu", "vf_attn_pp.cu", "vf_norm.cu", "vf_gemm.cu", "vf_gemm2.cu", "vf_conv_out.cu", "vf_linear.cu"]
+SOURCES = ["vf_capi.cu", "vf_ddim.cu", "vf_flow_warp.cu", "vf_fsai.cu", "vf_attn.cu", "vf_attn_f32.cu", "vf_attn_tc.cu", "vf_attn_stream.cu", "vf_attn_pp.cu", "vf_norm.cu", "vf_gemm.cu", "vf_gemm2.cu", "vf_gemm3.cu", "vf_conv_out.cu", "vf_linear.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -511,6 +511,93 @@ def linear_residual(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.
     return out
 
 
+_PROJ_KNOB = os.environ.get("VF_PROJ_TC", "1") != "0"     # 0: keep the 64x64-level projections on the library GEMM
+
+
+class _ProjFold:
+    """Per-weight constants of ops.linear_proj, cached until a parameter changes: the LayerNorm's gamma folded into
+    the weight columns (rounded to bf16 once), the fp32 column sums of THAT rounded matrix (so that the mean term
+    cancels exactly), and beta . W^T + bias in fp32."""
+    _cache = {}
+
+    @classmethod
+    def get(cls, weight, bias, ln):
+        ps = [weight] + ([bias] if bias is not None else []) + ([ln.weight, ln.bias] if ln is not None else [])
+        key = tuple((p.data_ptr(), p._version, p.dtype, p.device) for p in ps) + (bias is None, ln is None)
+        hit = cls._cache.get(key)
+        if hit is not None:
+            return hit
+        if len(cls._cache) > 512:
+            cls._cache.clear()
+        with torch.no_grad():
+            w32 = weight.detach().float()
+            b32 = bias.detach().float() if bias is not None else None
+            if ln is not None:
+                wg = (w32 * ln.weight.detach().float()[None, :]).to(torch.bfloat16).contiguous()
+                colsum = wg.float().sum(dim=1).contiguous()
+                lb = w32 @ ln.bias.detach().float()
+                b32 = lb if b32 is None else b32 + lb
+            else:
+                wg = weight.detach().contiguous()
+                colsum = None
+            b32 = b32.contiguous() if b32 is not None else None
+        hit = (wg, colsum, b32)
+        cls._cache[key] = hit
+        return hit
+
+
+def linear_proj_supported(x: torch.Tensor, weight: torch.Tensor) -> bool:
+    """Shapes / dtypes the tcgen05 projection kernel takes (k a multiple of 64 up to 320, n a multiple of 160, bf16)."""
+    n, k = weight.shape
+    return (_PROJ_KNOB and x.is_cuda and x.dtype == torch.bfloat16 and weight.dtype == torch.bfloat16 and x.shape[-1] == k
+            and k % 64 == 0 and k <= 320 and n % 160 == 0 and x.numel() // k >= 128)
+
+
+def linear_proj(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None,
+                residual: Optional[torch.Tensor] = None, ln=None, row_bias: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """LN(x) @ weight^T + bias + row_bias[sample] + residual as ONE tcgen05 kernel (csrc/vf_gemm3.cu).
+
+    ln: a torch.nn.LayerNorm over the last dimension of x (or None); x is then the RAW input -- mean / rstd are computed
+    inside the kernel, the normalised tensor never exists.  bias: (n,), the layer's own.  row_bias: (batch, n) for x of
+    shape (batch, tokens, k) -- one extra row per sample (attn2's single-token output), tokens % 128 == 0.
+    Replaces norm1 + to_q/to_k/to_v, to_out + adds, proj_in, proj_out + x_in of the 64x64 level
+    (ldm/modules/attention.py:172-176, 239-241, 261-288)."""
+    _need_cuda(x, weight, bias, residual, row_bias)
+    n, k = weight.shape
+    if x.shape[-1] != k or not x.is_contiguous() or x.dtype != torch.bfloat16 or weight.dtype != torch.bfloat16:
+        raise ValueError("linear_proj: x must be contiguous bf16 (..., k) and weight bf16 (n, k)")
+    if not weight.is_contiguous():
+        raise ValueError("linear_proj: weight must be contiguous")
+    rows = x.numel() // k
+    if residual is not None and (residual.shape != x.shape[:-1] + (n,) or residual.dtype != x.dtype or not residual.is_contiguous()):
+        raise ValueError("linear_proj: residual must be contiguous, of the output's shape and dtype")
+    if ln is not None and (tuple(ln.normalized_shape) != (k,) or ln.weight is None or ln.bias is None):
+        raise ValueError("linear_proj: ln must be an affine LayerNorm over the last dimension of x")
+    if ln is not None and residual is not None:
+        raise ValueError("linear_proj: the LayerNorm form takes no residual")
+    wg, colsum, b32 = _ProjFold.get(weight, bias, ln)
+    rpb = 0
+    if row_bias is not None:
+        if x.dim() != 3 or row_bias.shape != (x.shape[0], n):
+            raise ValueError("linear_proj: row_bias needs x (batch, tokens, k) and row_bias (batch, n)")
+        if x.shape[1] % 128:
+            raise ValueError("linear_proj: tokens per sample must be a multiple of 128 for a per-sample row")
+        rpb = x.shape[1]
+        rb = row_bias.float()
+        b32 = (rb + b32[None, :]).contiguous() if b32 is not None else rb.contiguous()
+    out = torch.empty(x.shape[:-1] + (n,), dtype=x.dtype, device=x.device)
+    lib = _LIB
+    units = (k + n + (n if residual is not None else 0)) * 2.0
+    _describe(f"linear_proj k={k} n={n}" + ("+ln" if ln is not None else "") + ("+res" if residual is not None else ""), units * rows)
+    rc = lib.vf_linear_proj(x.data_ptr(), wg.data_ptr(), b32.data_ptr() if b32 is not None else None, rpb,
+                            residual.data_ptr() if residual is not None else None,
+                            colsum.data_ptr() if colsum is not None else None, float(ln.eps) if ln is not None else 0.0,
+                            out.data_ptr(), rows, k, n, k, n, n, _code(x), _stream(x))
+    _lib.check(rc, "vf_linear_proj")
+    _count()
+    return out
+
+
 def conv3x3_out_f32(x_nhwc: torch.Tensor, conv) -> torch.Tensor:
     """The UNet's output convolution (openaimodel.py:835/:907) with an fp32 result: x_nhwc (n, h, w, c) bf16
     channels-last tokens -> (n, 4, h, w) fp32 contiguous.  eps leaves the network unrounded because classifier-free
