@@ -23,7 +23,7 @@
 //     exact in the fp32 accumulator), so it needs no second ring, no generic-proxy reads and no epilogue work, and is
 //     prefetched exactly as deep as A.  (The first version staged it next to the output: its two-deep ring exposed the L2
 //     latency of every box.)
-//   * output through a staging ring (4 x 8 KB, 64B swizzle) drained by TMA stores.  No row-per-thread global access anywhere
+//   * output through one 16 KB staging buffer per epilogue group, in steps of 64 / 64 / 32 columns, drained by TMA stores.  No row-per-thread global access anywhere
 //     (the failure mode of the first GEMM+GEGLU epilogue, profiles/r1_geglu_gemm_ncu.txt).
 //   * two accumulator sets of 160 TMEM columns: the epilogue of tile i runs under the MMAs of tile i + 1.
 //
@@ -109,7 +109,8 @@ struct P3Walk {
 template <bool kLN>
 __global__ void __launch_bounds__(kP3Threads, 1)
 proj3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
-             const __grid_constant__ CUtensorMap map_r, const __grid_constant__ CUtensorMap map_o, const Proj3Params P) {
+             const __grid_constant__ CUtensorMap map_r, const __grid_constant__ CUtensorMap map_o,
+             const __grid_constant__ CUtensorMap map_o32, const Proj3Params P) {
   // dynamic shared memory: [pad to 1024] | W (k_blocks x 20 KB) | A ring (5 x 16 KB) | staging (4 x 8 KB) | identity (8 KB) |
   //                        barriers | bias[2][160] | colsum[160] | stats[3][128]
   extern __shared__ unsigned char p3_smem[];
@@ -255,8 +256,9 @@ proj3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
     const int trow = quarter * 32 + lane;                   // row of the tile this thread owns
     const uint32_t sw = (uint32_t)(trow >> 1) & 3u;         // 64B swizzle of the staging rows
     const bool issuer = et == 0;
-    if (issuer) tma_prefetch_desc(&map_o);
-    uint32_t ti = 0, gs = 0;
+    const bool has_bias = P.bias != nullptr;
+    if (issuer) { tma_prefetch_desc(&map_o); tma_prefetch_desc(&map_o32); }
+    uint32_t ti = 0;
     P3Walk tw(P);
     if (kLN)
       for (int i = et; i < kP3BN; i += 128) s_cs[i] = P.colsum[tw.nb * kP3BN + i];
@@ -279,42 +281,64 @@ proj3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
       mbar_wait(&bars.acc_full[ab], (ti >> 1) & 1);
       tc_fence_after();
       const uint32_t acc = tmem + ab * 256 + lane_off;
+      // three column steps per tile: 64, 64 and 32 columns.  The staging rows are as wide as the step (128-byte rows with
+      // the 128B swizzle, 64-byte rows with the 64B swizzle for the last one): the TMA store engine takes a fixed time per
+      // box ROW, and 64-byte rows capped the first version of this epilogue at ~10 B/clk/SM (3900 cycles per 40 KB tile for
+      // every shape, profiles/r2_proj_v2_ncu.txt).  One 16 KB buffer per group; the drain of step i overlaps the TMEM loads
+      // and the arithmetic of step i + 1.
+      unsigned char* obuf = out_stage + (size_t)grp * (2 * kP3OutBytes);
 #pragma unroll 1
-      for (int c = 0; c < kP3Steps; ++c, ++gs) {
-        const uint32_t b = grp * 2 + (gs & 1);
-        unsigned char* obuf = out_stage + (size_t)b * kP3OutBytes;
-        uint32_t v[32];
-        tmem_ld_x32(acc + c * 32, v);
-        if (issuer) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");     // the group's store of two steps ago has drained it
-        p3_bar_sync(bar0 + 1, 128);
-        tmem_wait_ld();
-        uint32_t pk[16];
+      for (int st = 0; st < 3; ++st) {
+        const int c0 = st * 64;
+        const int halves = st < 2 ? 2 : 1;
+        uint32_t pk[32];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
+        for (int h = 0; h < 2; ++h) {
+          if (h < halves) {
+            uint32_t v[32];
+            tmem_ld_x32(acc + c0 + h * 32, v);
+            tmem_wait_ld();
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int i = q * 8 + j * 2;
-            const float2 bb = *reinterpret_cast<const float2*>(&s_bias[ab][c * 32 + i]);           // broadcast reads
-            float2 a = make_float2(__uint_as_float(v[i]), __uint_as_float(v[i + 1]));
-            float2 add = bb;
-            if (kLN) {
-              const float2 cs = *reinterpret_cast<const float2*>(&s_cs[c * 32 + i]);
-              add = __ffma2_rn(make_float2(mu_rs, mu_rs), cs, bb);                                  // bias - mean rstd colsum
-              a = __ffma2_rn(make_float2(rs, rs), a, add);
-            } else {
-              a = __fadd2_rn(a, add);
+            for (int j = 0; j < 8; ++j) {
+              // four columns per iteration: one 16-byte broadcast read per constant vector (the shared-memory pipe, which
+              // also feeds the tensor core's operands, is the busiest unit of this kernel)
+              const int i = j * 4;
+              float2 a0 = make_float2(__uint_as_float(v[i]), __uint_as_float(v[i + 1]));
+              float2 a1 = make_float2(__uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]));
+              float4 bb = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+              if (kLN || has_bias) bb = *reinterpret_cast<const float4*>(&s_bias[ab][c0 + h * 32 + i]);
+              if (kLN) {
+                const float4 cs = *reinterpret_cast<const float4*>(&s_cs[c0 + h * 32 + i]);
+                const float2 m2 = make_float2(mu_rs, mu_rs), r2 = make_float2(rs, rs);
+                a0 = __ffma2_rn(r2, a0, __ffma2_rn(m2, make_float2(cs.x, cs.y), make_float2(bb.x, bb.y)));      // rstd acc + (bias - mean rstd colsum)
+                a1 = __ffma2_rn(r2, a1, __ffma2_rn(m2, make_float2(cs.z, cs.w), make_float2(bb.z, bb.w)));
+              } else if (has_bias) {
+                a0 = __fadd2_rn(a0, make_float2(bb.x, bb.y));
+                a1 = __fadd2_rn(a1, make_float2(bb.z, bb.w));
+              }
+              pk[h * 16 + j * 2] = pack_bf16(a0.x, a0.y);
+              pk[h * 16 + j * 2 + 1] = pack_bf16(a1.x, a1.y);
             }
-            pk[q * 4 + j] = pack_bf16(a.x, a.y);
           }
         }
+        if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");     // the group's previous store has drained the buffer
+        p3_bar_sync(bar0 + 1, 128);
+        if (st < 2) {
+          const uint32_t sw8 = (uint32_t)trow & 7u;           // 128B swizzle: 16-byte chunk q of row r sits at chunk q ^ (r & 7)
 #pragma unroll
-        for (int q = 0; q < 4; ++q)
-          *reinterpret_cast<uint4*>(obuf + trow * 64 + ((q ^ sw) << 4)) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+          for (int q = 0; q < 8; ++q)
+            *reinterpret_cast<uint4*>(obuf + trow * 128 + ((q ^ sw8) << 4)) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+        } else {
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            *reinterpret_cast<uint4*>(obuf + trow * 64 + ((q ^ sw) << 4)) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+        }
         fence_proxy_async();
         p3_bar_sync(bar0 + 2, 128);
         if (issuer) {
+          const CUtensorMap* mo = st < 2 ? &map_o : &map_o32;
           asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
-                       :: "l"(reinterpret_cast<uint64_t>(&map_o)), "r"(tw.nb * kP3BN + c * 32), "r"(tw.cur * kP3BM), "r"(smem_u32(obuf))
+                       :: "l"(reinterpret_cast<uint64_t>(mo)), "r"(tw.nb * kP3BN + c0), "r"(tw.cur * kP3BM), "r"(smem_u32(obuf))
                        : "memory");
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
@@ -442,7 +466,9 @@ extern "C" int vf_linear_proj(const void* x, const void* w, const float* bias, l
   CUtensorMap ma, mw, mr, mo;
   if (int rc = p3_make_map(&ma, x, rows, k, ld_x, kP3BK, kP3BM, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B)) return rc;
   if (int rc = p3_make_map(&mw, w, n, k, k, kP3BK, kP3BN, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B)) return rc;
-  if (int rc = p3_make_map(&mo, out, rows, n, ld_out, 32, kP3BM, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE)) return rc;
+  CUtensorMap mo32;
+  if (int rc = p3_make_map(&mo, out, rows, n, ld_out, 64, kP3BM, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE)) return rc;
+  if (int rc = p3_make_map(&mo32, out, rows, n, ld_out, 32, kP3BM, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE)) return rc;
   if (residual) {
     if (int rc = p3_make_map(&mr, residual, rows, n, ld_res, kP3BK, kP3BM, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B)) return rc;
   } else {
@@ -465,7 +491,7 @@ extern "C" int vf_linear_proj(const void* x, const void* w, const float* bias, l
   if (groups > P.m_blocks) groups = P.m_blocks;
   if (groups < 1) groups = 1;
   const int grid = groups * P.n_blocks;
-  if (ln) proj3_kernel<true><<<grid, kP3Threads, smem, (cudaStream_t)stream>>>(ma, mw, mr, mo, P);
-  else proj3_kernel<false><<<grid, kP3Threads, smem, (cudaStream_t)stream>>>(ma, mw, mr, mo, P);
+  if (ln) proj3_kernel<true><<<grid, kP3Threads, smem, (cudaStream_t)stream>>>(ma, mw, mr, mo, mo32, P);
+  else proj3_kernel<false><<<grid, kP3Threads, smem, (cudaStream_t)stream>>>(ma, mw, mr, mo, mo32, P);
   return check_cuda(cudaGetLastError(), "proj3_kernel launch");
 }

@@ -123,6 +123,7 @@ def register_spa_attn_injection(model, injection_schedule, switch_on=True, input
                                 ops.flow_warp_blend(sk[:1], fl[:1], alpha, FLOW_HW, FLOW_HW, prev_halo=halo_k, out=cond_k[:1])
             return self.project_out(self.attend(q, k, v))
 
+        forward._vf_native = True      # uses `x` only through project_qkv: BasicTransformerBlock may fold norm1 into it
         return forward
 
     unet = model.model.model.diffusion_model

@@ -96,9 +96,24 @@ class CrossAttention(nn.Module):
 
     def project_qkv(self, x):
         """Self-attention projections in one GEMM: returns column-slice views q, k, v of a
-        (batch, n, 3*inner) buffer (row stride 3*inner; the kernels take row strides)."""
+        (batch, n, 3*inner) buffer (row stride 3*inner; the kernels take row strides).
+
+        When the enclosing BasicTransformerBlock has armed `_pre_ln` (its norm1), `x` is the block's RAW input and the
+        LayerNorm happens inside the projection kernel (ops.linear_proj: the normalised tensor never exists) or, for
+        shapes that kernel does not take, right here."""
         inner = self.heads * self.dim_head
-        qkv = F.linear(x, self.fused_qkv_weight())
+        w = self.fused_qkv_weight()
+        ln = getattr(self, "_pre_ln", None)
+        if ln is not None:
+            object.__setattr__(self, "_pre_ln", None)       # (object.__setattr__: a Module value must not become a sub-module)
+            if ops.linear_proj_supported(x, w):
+                qkv = ops.linear_proj(x.contiguous(), w, ln=ln)
+            else:
+                qkv = F.linear(ops.add_layer_norm(x.contiguous(), ln.weight, ln.bias, ln.eps), w)
+        elif ops.linear_proj_supported(x, w) and x.dim() == 3:
+            qkv = ops.linear_proj(x.contiguous(), w)
+        else:
+            qkv = F.linear(x, w)
         return qkv[..., :inner], qkv[..., inner:2 * inner], qkv[..., 2 * inner:]
 
     def attend(self, q, k, v):
@@ -114,6 +129,9 @@ class CrossAttention(nn.Module):
         if ep is not None and not ep.done and a.dtype == torch.bfloat16 and a.dim() == 3 and a.shape[1] >= 256:
             lin = self.to_out[0]
             ep.done = True
+            if ops.linear_proj_supported(a, lin.weight) and a.shape[1] % 128 == 0 and lin.weight.is_contiguous():
+                # 64x64 level: the tcgen05 projection kernel (bias and per-sample row in fp32, residual through the MMA)
+                return ops.linear_proj(a.contiguous(), lin.weight, None if ep.prebiased else lin.bias, ep.residual, row_bias=ep.row)
             bias = ep.row if ep.prebiased else (lin.bias + ep.row).contiguous()
             return ops.linear_residual(a.contiguous(), lin.weight, bias, ep.residual)
         return self.to_out(a)
@@ -141,6 +159,7 @@ class CrossAttention(nn.Module):
 
 import os as _os
 _FUSE_TO_OUT = _os.environ.get("VF_FUSE_TO_OUT", "1") != "0"     # tuning knob: 0 keeps to_out and the LN3 add separate
+_FUSE_LN_QKV = _os.environ.get("VF_FUSE_LN_QKV", "1") != "0"     # tuning knob: 0 keeps norm1 as its own kernel
 
 
 class _FusedOut:
@@ -189,6 +208,22 @@ class BasicTransformerBlock(nn.Module):
             self.__dict__["_row_gemm"] = hit
         return F.linear(context[:, 0], hit[1], hit[2])
 
+    def _attn1_of_norm1(self, x, ln):
+        """attn1(norm1(x)) (reference :239).  bf16 with this package's own attn1 forward (the class's, or the VFace hook
+        closure of ldm/models/pnp_utils.py, both of which use their input only through project_qkv): norm1 is handed to
+        project_qkv and folded into the QKV projection kernel; a foreign `forward` gets the normalised tensor as before."""
+        a1 = self.attn1
+        fwd = a1.__dict__.get("forward")
+        own = fwd is None or getattr(fwd, "_vf_native", False)
+        if (_FUSE_LN_QKV and own and type(a1) is CrossAttention and x.dtype == torch.bfloat16 and x.dim() == 3
+                and type(self.norm1) is nn.LayerNorm and ops.linear_proj_supported(x, a1.to_q.weight)):
+            object.__setattr__(a1, "_pre_ln", self.norm1)
+            try:
+                return a1(x)
+            finally:
+                object.__setattr__(a1, "_pre_ln", None)
+        return a1(ln(self.norm1, x))
+
     def _forward(self, x, context=None):
         """x = attn1(LN1(x)) + x ; x = attn2(LN2(x), ctx) + x ; x = ff(LN3(x)) + x   (reference :239-243),
         with each residual add fused into the following LayerNorm (one pass instead of two)."""
@@ -212,7 +247,7 @@ class BasicTransformerBlock(nn.Module):
                     ep = _FusedOut(x, row)
             self.attn1._fused_out = ep
             try:
-                a1 = self.attn1(ln(self.norm1, x))
+                a1 = self._attn1_of_norm1(x, ln)
             finally:
                 self.attn1._fused_out = None
             if ep is not None and ep.done:
@@ -223,7 +258,7 @@ class BasicTransformerBlock(nn.Module):
                     row = self.attn2.single_token_row(context)[:, 0]
                 x, n3 = ln(self.norm3, x, y=a1.contiguous(), row_bias=row)
             return self._ff_residual(x, n3)
-        a1 = self.attn1(ln(self.norm1, x))
+        a1 = self._attn1_of_norm1(x, ln)
         x, n2 = ln(self.norm2, x, y=a1.contiguous())
         a2 = self.attn2(n2, context=context)
         x, n3 = ln(self.norm3, x, y=a2.contiguous())
@@ -261,11 +296,17 @@ class SpatialTransformer(nn.Module):
         tok = x.permute(0, 2, 3, 1)                              # NHWC view: free for channels_last
         tok = tok.contiguous().view(b, h * w, c)
         g = ops.group_norm_nhwc(tok, self.norm.weight, self.norm.bias, self.norm.eps, self.norm.num_groups)
-        t = F.linear(g, self.proj_in.weight.reshape(self.proj_in.out_channels, c), self.proj_in.bias)   # 1x1 conv
+        w_in = self.proj_in.weight.reshape(self.proj_in.out_channels, c)                                # 1x1 conv
+        if ops.linear_proj_supported(g, w_in) and w_in.is_contiguous():
+            t = ops.linear_proj(g, w_in, self.proj_in.bias)
+        else:
+            t = F.linear(g, w_in, self.proj_in.bias)
         for block in self.transformer_blocks:
             t = block(t, context=context)
         w_out = self.proj_out.weight.reshape(c, -1)                                                     # 1x1 conv
-        if t.dtype == torch.bfloat16 and w_out.is_contiguous():
+        if ops.linear_proj_supported(t, w_out) and w_out.is_contiguous():
+            out = ops.linear_proj(t.contiguous(), w_out, self.proj_out.bias, tok)            # proj_out(t) + x_in, tcgen05 kernel
+        elif t.dtype == torch.bfloat16 and w_out.is_contiguous():
             out = ops.linear_residual(t.contiguous(), w_out, self.proj_out.bias, tok)    # proj_out(t) + x_in in one GEMM
         else:
             out = ops.add_bias(F.linear(t, w_out, self.proj_out.bias), tok)
