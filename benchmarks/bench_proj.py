@@ -38,6 +38,12 @@ t, _ = time_kernel(lambda: ops.linear_proj(x, wq, None, None, ln=ln))
 line("linear_proj LN + QKV, one launch", t, 4)
 t, _ = time_kernel(lambda: ops.linear_proj(xn, wq))
 line("linear_proj QKV without LN", t, 4)
+_, st = ops.linear_proj(a, wo, bo, emit_stats=True)
+xs = ops.linear_proj(a, wo, bo)
+t, _ = time_kernel(lambda: ops.linear_proj(xs, wq, None, None, ln=ln, ln_stats=st))
+line("linear_proj LN + QKV, statistics handed over", t, 4)
+t, _ = time_kernel(lambda: ops.linear_proj(a, wo, bo, emit_stats=True))
+line("linear_proj proj_in + bias + emitted statistics", t, 2)
 rb = (bo.float()[None] + row.float()).bfloat16().contiguous()
 t, _ = time_kernel(lambda: ops.linear_residual(a, wo, rb, x))
 line("cuBLASLt to_out + per-sample row + residual (batched)", t, 3)

@@ -33,7 +33,7 @@ extern "C" {
 #define VF_F32 0
 #define VF_BF16 1
 
-#define VF_ABI_VERSION 9
+#define VF_ABI_VERSION 10
 
 /* ABI version of the loaded library (== VF_ABI_VERSION). */
 int vf_abi_version(void);
@@ -247,13 +247,18 @@ int vf_linear_residual_batched(const void* x, const void* w, const void* bias, c
  *   bias       fp32, (n) with rows_per_bias = 0, or (rows / rows_per_bias, n) with rows_per_bias % 128 == 0; may be NULL.
  *   residual   bf16 (rows, n), row stride ld_res, or NULL (not together with ln_colsum).  out (rows, n) bf16, row stride
  *              ld_out; no aliasing.
+ *   stats_out  optional (rows, n / 160, 2) fp32: per row and 160-column slice, {sum, sum of squares} of the bf16 OUTPUT
+ *              values (not in the LayerNorm form).  ln_stats_in: the same array written by the call that produced x
+ *              ((rows, ln_stats_parts, 2), partials summed here): mean / rstd then come from it instead of a second look
+ *              at x -- the LayerNorm statistics are a by-product of the producer's epilogue.  NULL: computed in-kernel.
  * k a multiple of 64 up to 320, n a multiple of 160 (vf_linear_proj_supported), bf16 only; other shapes and fp32 stay on
  * the library GEMM (vf_linear_residual).
  */
 int vf_linear_proj_supported(long long rows, int k, int n);
 int vf_linear_proj(const void* x, const void* w, const float* bias, long long rows_per_bias, const void* residual,
-                   const float* ln_colsum, float ln_eps, void* out, long long rows, int k, int n, long long ld_x,
-                   long long ld_res, long long ld_out, int dtype, void* stream);
+                   const float* ln_colsum, float ln_eps, const float* ln_stats_in, int ln_stats_parts, float* stats_out,
+                   void* out, long long rows, int k, int n, long long ld_x, long long ld_res, long long ld_out, int dtype,
+                   void* stream);
 
 #ifdef __cplusplus
 }

@@ -86,7 +86,7 @@ def test_linear_proj_ragged_rows_and_untouched_tail():
     # guard rows: call the C-ABI on a view of a larger buffer
     buf = torch.full((rows + 64, n), 7.0, dtype=torch.bfloat16, device=_dev())
     lib = _lib.load()
-    rc = lib.vf_linear_proj(x.data_ptr(), w.data_ptr(), None, 0, r.data_ptr(), None, 0.0,
+    rc = lib.vf_linear_proj(x.data_ptr(), w.data_ptr(), None, 0, r.data_ptr(), None, 0.0, None, 0, None,
                             buf.data_ptr(), rows, k, n, k, n, n, _lib.VF_BF16, torch.cuda.current_stream().cuda_stream)
     assert rc == 0, lib.vf_last_error()
     torch.cuda.synchronize()
@@ -108,6 +108,32 @@ def test_linear_proj_residual_is_added_exactly():
     r = _mk((3, 256, 960), 42, 3.0)
     w = torch.zeros(960, 320, dtype=torch.bfloat16, device=_dev())
     assert torch.equal(ops.linear_proj(x, w, None, r), r)
+
+
+@pytest.mark.parametrize("rows", [4096, 1000])
+def test_linear_proj_row_statistics_hand_over(rows):
+    """proj_in's epilogue emits {sum, sum of squares} of its bf16 output rows per 160-column slice; the next projection's
+    LayerNorm takes mean / rstd from them (SpatialTransformer -> BasicTransformerBlock.norm1 -> to_q/k/v,
+    attention.py:279,239,172-174).  The emitted numbers are exact sums of the stored values (fp32 accumulation), and the
+    handed-over form matches the fp64 reference as well as the in-kernel form does."""
+    from vface_b200 import ops
+    g = _mk((rows, 320), 51, 1.2, 0.3)
+    w_in, b_in = _mk((320, 320), 52, 320 ** -0.5), _mk((320,), 53, 0.4)
+    t, st = ops.linear_proj(g, w_in, b_in, emit_stats=True)
+    assert st.shape == (rows, 2, 2) and torch.equal(t, ops.linear_proj(g, w_in, b_in))
+    td = t.double()
+    want_sum = torch.stack([td[:, :160].sum(1), td[:, 160:].sum(1)], 1)
+    want_sq = torch.stack([(td[:, :160] ** 2).sum(1), (td[:, 160:] ** 2).sum(1)], 1)
+    assert (st[..., 0].double() - want_sum).abs().max().item() < 1e-3
+    assert ((st[..., 1].double() - want_sq).abs() / want_sq).max().item() < 1e-5
+    ln = _ln(320, 54)
+    wq = _mk((960, 320), 55, 320 ** -0.5)
+    got = ops.linear_proj(t, wq, ln=ln, ln_stats=st)
+    ref = _ref(t, wq, None, None, ln, None)
+    rel = ((got.double() - ref).norm() / ref.norm()).item()
+    assert rel < 3 * 2.0 ** -9, rel
+    own = ops.linear_proj(t, wq, ln=ln)
+    assert (got.float() - own.float()).abs().max().item() <= 2.0 ** -7 * max(1.0, ref.abs().max().item())
 
 
 def test_linear_proj_large_mean_rows():

@@ -10,7 +10,7 @@ import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libvface_b200.so")
-ABI_VERSION = 9
+ABI_VERSION = 10
 
 VF_F32 = 0
 VF_BF16 = 1
@@ -43,7 +43,7 @@ SIGNATURES = {
     "vf_conv3x3_out_f32": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "vf_linear_residual": (_i, [_vp, _vp, _vp, _vp, _vp, _ll, _i, _i, _ll, _ll, _ll, _vp, _ll, _i, _vp]),
     "vf_linear_proj_supported": (_i, [_ll, _i, _i]),
-    "vf_linear_proj": (_i, [_vp, _vp, _vp, _ll, _vp, _vp, _f, _vp, _ll, _i, _i, _ll, _ll, _ll, _i, _vp]),
+    "vf_linear_proj": (_i, [_vp, _vp, _vp, _ll, _vp, _vp, _f, _vp, _i, _vp, _vp, _ll, _i, _i, _ll, _ll, _ll, _i, _vp]),
     "vf_linear_residual_batched": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _ll, _i, _i, _ll, _ll, _ll, _vp, _ll, _i, _vp]),
 }
 

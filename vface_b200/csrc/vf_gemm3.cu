@@ -61,6 +61,9 @@ constexpr int kP3Steps = kP3BN / 32;                      // column steps of the
 struct Proj3Params {
   const float* bias;               // (bias_rows, n) fp32 or null
   const float* colsum;             // (n) fp32: sum over k of the (gamma-folded, bf16) weight row; LayerNorm form only
+  const float2* stats_in;          // kLN == 2: (rows, stats_parts) partial {sum, sum of squares} of the input rows
+  float2* stats_out;               // kEmit: (rows, n_blocks) partial {sum, sum of squares} of the bf16 OUTPUT rows
+  int stats_parts;
   long long rows;
   long long rows_per_bias;         // 0: one bias row for all; else rows sharing one bias row (multiple of 128)
   int n, k;
@@ -106,7 +109,10 @@ struct P3Walk {
   __device__ void next() { cur += step; }
 };
 
-template <bool kLN>
+// kLN: 0 no normalisation, 1 row statistics computed here (stats warps), 2 row statistics handed over by the kernel that
+// produced x (its kEmit epilogue).  kEmit: the epilogue also writes {sum, sum of squares} of every bf16 output row of its
+// 160-column slice, so that a LayerNorm over the output (the next projection's kLN == 2) needs no pass of its own.
+template <int kLN, bool kEmit>
 __global__ void __launch_bounds__(kP3Threads, 1)
 proj3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
              const __grid_constant__ CUtensorMap map_r, const __grid_constant__ CUtensorMap map_o,
@@ -131,7 +137,7 @@ proj3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kP3Stages; ++s) {
       mbar_init(&bars.full[s], 1);
-      mbar_init(&bars.empty[s], kLN ? 5 : 1);               // the MMA commit (+ one arrival per stats warp)
+      mbar_init(&bars.empty[s], kLN == 1 ? 5 : 1);               // the MMA commit (+ one arrival per stats warp)
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&bars.acc_full[a], 1);
@@ -272,12 +278,25 @@ proj3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
         p3_bar_sync(bar0, 128);
       }
       float mu_rs = 0.0f, rs = 1.0f;                        // -mean * rstd, rstd
-      if (kLN) {
+      const long long grow = (long long)tw.cur * kP3BM + trow;      // this thread's row of the tensor
+      if (kLN == 1) {
         mbar_wait(&bars.stats_full[ti % 3], (ti / 3) & 1);
         const float2 st = s_stats[ti % 3][trow];
         rs = st.y;
         mu_rs = -st.x * st.y;
+      } else if (kLN == 2) {
+        float sx = 0.0f, sq = 0.0f;
+        if (grow < P.rows)
+          for (int j = 0; j < P.stats_parts; ++j) {
+            const float2 pp = P.stats_in[grow * P.stats_parts + j];
+            sx += pp.x;
+            sq += pp.y;
+          }
+        const float mean = sx * P.inv_k;
+        rs = rsqrtf(fmaxf(sq * P.inv_k - mean * mean, 0.0f) + P.eps);
+        mu_rs = -mean * rs;
       }
+      float2 e_sum = make_float2(0.0f, 0.0f), e_sq = make_float2(0.0f, 0.0f);
       mbar_wait(&bars.acc_full[ab], (ti >> 1) & 1);
       tc_fence_after();
       const uint32_t acc = tmem + ab * 256 + lane_off;
@@ -316,8 +335,14 @@ proj3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
                 a0 = __fadd2_rn(a0, make_float2(bb.x, bb.y));
                 a1 = __fadd2_rn(a1, make_float2(bb.z, bb.w));
               }
-              pk[h * 16 + j * 2] = pack_bf16(a0.x, a0.y);
-              pk[h * 16 + j * 2 + 1] = pack_bf16(a1.x, a1.y);
+              const uint32_t p0 = pack_bf16(a0.x, a0.y), p1 = pack_bf16(a1.x, a1.y);
+              pk[h * 16 + j * 2] = p0;
+              pk[h * 16 + j * 2 + 1] = p1;
+              if (kEmit) {                                    // statistics of the ROUNDED values: what the consumer will read
+                const float2 r0 = make_float2(bf16lo(p0), bf16hi(p0)), r1 = make_float2(bf16lo(p1), bf16hi(p1));
+                e_sum = __fadd2_rn(e_sum, __fadd2_rn(r0, r1));
+                e_sq = __ffma2_rn(r0, r0, __ffma2_rn(r1, r1, e_sq));
+              }
             }
           }
         }
@@ -343,12 +368,13 @@ proj3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
       }
+      if (kEmit && grow < P.rows) P.stats_out[grow * P.n_blocks + tw.nb] = make_float2(e_sum.x + e_sum.y, e_sq.x + e_sq.y);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars.acc_empty[ab]);
     }
     if (issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");      // stores complete before exit
-  } else if (kLN && warp >= 12) {
+  } else if (kLN == 1 && warp >= 12) {
     // =========================== row statistics (LayerNorm form) ===========================================
     const int row = (warp - 12) * 32 + lane;
     const uint32_t swz = (uint32_t)row & 7u;                // 128B swizzle of the A k-block rows
@@ -428,7 +454,8 @@ extern "C" int vf_linear_proj_supported(long long rows, int k, int n) {
 }
 
 extern "C" int vf_linear_proj(const void* x, const void* w, const float* bias, long long rows_per_bias, const void* residual,
-                              const float* ln_colsum, float ln_eps, void* out, long long rows, int k, int n, long long ld_x,
+                              const float* ln_colsum, float ln_eps, const float* ln_stats_in, int ln_stats_parts,
+                              float* stats_out, void* out, long long rows, int k, int n, long long ld_x,
                               long long ld_res, long long ld_out, int dtype, void* stream) {
   using namespace vf;
   if (int rc = check_device()) return rc;
@@ -442,6 +469,11 @@ extern "C" int vf_linear_proj(const void* x, const void* w, const float* bias, l
   if (rows_per_bias < 0 || (rows_per_bias > 0 && (!bias || rows_per_bias % kP3BM)))
     return fail("vf_linear_proj: rows_per_bias %lld must be a multiple of %d (and needs a bias)", rows_per_bias, kP3BM);
   if (out == residual || out == x) return fail("vf_linear_proj: out must not alias x or residual");
+  if (ln_stats_in && (!ln_colsum || ln_stats_parts < 1 || ln_stats_parts > 16))
+    return fail("vf_linear_proj: ln_stats_in needs the LayerNorm form and 1..16 partials per row (got %d)", ln_stats_parts);
+  if (stats_out && ln_colsum) return fail("vf_linear_proj: stats_out is not available in the LayerNorm form");
+  if ((reinterpret_cast<uintptr_t>(ln_stats_in) | reinterpret_cast<uintptr_t>(stats_out)) & 7)
+    return fail("vf_linear_proj: row statistics must be 8-byte aligned");
   if (residual && ln_colsum) return fail("vf_linear_proj: the LayerNorm form takes no residual (it would be scaled by rstd inside the accumulator)");
   const void* ptrs[4] = {x, w, out, residual};
   for (const void* p : ptrs)
@@ -450,6 +482,9 @@ extern "C" int vf_linear_proj(const void* x, const void* w, const float* bias, l
   Proj3Params P;
   P.bias = bias;
   P.colsum = ln_colsum;
+  P.stats_in = reinterpret_cast<const float2*>(ln_stats_in);
+  P.stats_out = reinterpret_cast<float2*>(stats_out);
+  P.stats_parts = ln_stats_parts;
   P.rows = rows;
   P.rows_per_bias = rows_per_bias;
   P.n = n; P.k = k;
@@ -480,18 +515,19 @@ extern "C" int vf_linear_proj(const void* x, const void* w, const float* bias, l
   if (smem > 232448) return fail("vf_linear_proj: shared-memory plan %zu exceeds the 227 KB of an SM", smem);
   int dev = 0;
   VF_CUDA_TRY(cudaGetDevice(&dev));
-  static size_t attr_dev[64][2] = {};
-  const int ln = ln_colsum ? 1 : 0;
-  if (dev < 64 && smem > attr_dev[dev][ln]) {
-    if (ln) VF_CUDA_TRY(cudaFuncSetAttribute(proj3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    else VF_CUDA_TRY(cudaFuncSetAttribute(proj3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_dev[dev][ln] = smem;
+  // variant: 0 plain, 1 plain + emitted statistics, 2 LayerNorm with in-kernel statistics, 3 LayerNorm with handed-over statistics
+  const int variant = ln_colsum ? (ln_stats_in ? 3 : 2) : (stats_out ? 1 : 0);
+  typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const Proj3Params);
+  static const KernelFn kernels[4] = {proj3_kernel<0, false>, proj3_kernel<0, true>, proj3_kernel<1, false>, proj3_kernel<2, false>};
+  static size_t attr_dev[64][4] = {};
+  if (dev < 64 && smem > attr_dev[dev][variant]) {
+    VF_CUDA_TRY(cudaFuncSetAttribute(kernels[variant], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_dev[dev][variant] = smem;
   }
   int groups = num_sms() / P.n_blocks;
   if (groups > P.m_blocks) groups = P.m_blocks;
   if (groups < 1) groups = 1;
   const int grid = groups * P.n_blocks;
-  if (ln) proj3_kernel<true><<<grid, kP3Threads, smem, (cudaStream_t)stream>>>(ma, mw, mr, mo, mo32, P);
-  else proj3_kernel<false><<<grid, kP3Threads, smem, (cudaStream_t)stream>>>(ma, mw, mr, mo, mo32, P);
+  kernels[variant]<<<grid, kP3Threads, smem, (cudaStream_t)stream>>>(ma, mw, mr, mo, mo32, P);
   return check_cuda(cudaGetLastError(), "proj3_kernel launch");
 }

@@ -107,7 +107,11 @@ class CrossAttention(nn.Module):
         if ln is not None:
             object.__setattr__(self, "_pre_ln", None)       # (object.__setattr__: a Module value must not become a sub-module)
             if ops.linear_proj_supported(x, w):
-                qkv = ops.linear_proj(x.contiguous(), w, ln=ln)
+                # row statistics handed over by the kernel that produced x (SpatialTransformer's proj_in), if any
+                st = getattr(x, "_vf_row_stats", None) if _STATS_HANDOFF else None
+                if st is not None and (st.shape[0] != x.numel() // x.shape[-1] or st.device != x.device):
+                    st = None
+                qkv = ops.linear_proj(x.contiguous(), w, ln=ln, ln_stats=st)
             else:
                 qkv = F.linear(ops.add_layer_norm(x.contiguous(), ln.weight, ln.bias, ln.eps), w)
         elif ops.linear_proj_supported(x, w) and x.dim() == 3:
@@ -159,6 +163,7 @@ class CrossAttention(nn.Module):
 
 import os as _os
 _FUSE_TO_OUT = _os.environ.get("VF_FUSE_TO_OUT", "1") != "0"     # tuning knob: 0 keeps to_out and the LN3 add separate
+_STATS_HANDOFF = _os.environ.get("VF_PROJ_STATS", "1") != "0"    # tuning knob: 0 = norm1's statistics computed inside the QKV kernel
 _FUSE_LN_QKV = _os.environ.get("VF_FUSE_LN_QKV", "1") != "0"     # tuning knob: 0 keeps norm1 as its own kernel
 
 
@@ -298,7 +303,13 @@ class SpatialTransformer(nn.Module):
         g = ops.group_norm_nhwc(tok, self.norm.weight, self.norm.bias, self.norm.eps, self.norm.num_groups)
         w_in = self.proj_in.weight.reshape(self.proj_in.out_channels, c)                                # 1x1 conv
         if ops.linear_proj_supported(g, w_in) and w_in.is_contiguous():
-            t = ops.linear_proj(g, w_in, self.proj_in.bias)
+            if _STATS_HANDOFF and _FUSE_LN_QKV and w_in.shape[0] <= 320:
+                # the epilogue also emits sum / sum of squares of every output row: the first block's norm1 (folded into its
+                # QKV projection) then needs no pass over `t` of its own
+                t, st = ops.linear_proj(g, w_in, self.proj_in.bias, emit_stats=True)
+                t._vf_row_stats = st
+            else:
+                t = ops.linear_proj(g, w_in, self.proj_in.bias)
         else:
             t = F.linear(g, w_in, self.proj_in.bias)
         for block in self.transformer_blocks:

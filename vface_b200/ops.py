@@ -554,12 +554,15 @@ def linear_proj_supported(x: torch.Tensor, weight: torch.Tensor) -> bool:
 
 
 def linear_proj(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None,
-                residual: Optional[torch.Tensor] = None, ln=None, row_bias: Optional[torch.Tensor] = None) -> torch.Tensor:
+                residual: Optional[torch.Tensor] = None, ln=None, row_bias: Optional[torch.Tensor] = None,
+                ln_stats: Optional[torch.Tensor] = None, emit_stats: bool = False):
     """LN(x) @ weight^T + bias + row_bias[sample] + residual as ONE tcgen05 kernel (csrc/vf_gemm3.cu).
 
     ln: a torch.nn.LayerNorm over the last dimension of x (or None); x is then the RAW input -- mean / rstd are computed
     inside the kernel, the normalised tensor never exists.  bias: (n,), the layer's own.  row_bias: (batch, n) for x of
     shape (batch, tokens, k) -- one extra row per sample (attn2's single-token output), tokens % 128 == 0.
+    emit_stats: also return (rows, n / 160, 2) fp32 partial {sum, sum of squares} of the bf16 output rows; handed to the
+    NEXT projection as ln_stats, its LayerNorm needs no look at x of its own (returns (out, stats)).
     Replaces norm1 + to_q/to_k/to_v, to_out + adds, proj_in, proj_out + x_in of the 64x64 level
     (ldm/modules/attention.py:172-176, 239-241, 261-288)."""
     _need_cuda(x, weight, bias, residual, row_bias)
@@ -585,17 +588,29 @@ def linear_proj(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tens
         rpb = x.shape[1]
         rb = row_bias.float()
         b32 = (rb + b32[None, :]).contiguous() if b32 is not None else rb.contiguous()
+    parts = 0
+    if ln_stats is not None:
+        if ln is None or ln_stats.dtype != torch.float32 or not ln_stats.is_contiguous() or ln_stats.dim() != 3 \
+                or ln_stats.shape[0] != rows or ln_stats.shape[2] != 2 or ln_stats.device != x.device:
+            raise ValueError("linear_proj: ln_stats must be the (rows, parts, 2) fp32 array emitted for x, and needs ln")
+        parts = ln_stats.shape[1]
+    if emit_stats and ln is not None:
+        raise ValueError("linear_proj: emit_stats is not available in the LayerNorm form")
+    stats = torch.empty((rows, n // 160, 2), dtype=torch.float32, device=x.device) if emit_stats else None
     out = torch.empty(x.shape[:-1] + (n,), dtype=x.dtype, device=x.device)
     lib = _LIB
     units = (k + n + (n if residual is not None else 0)) * 2.0
-    _describe(f"linear_proj k={k} n={n}" + ("+ln" if ln is not None else "") + ("+res" if residual is not None else ""), units * rows)
+    _describe(f"linear_proj k={k} n={n}" + ("+ln" if ln is not None else "") + ("(stats in)" if ln_stats is not None else "")
+              + ("+res" if residual is not None else "") + ("+stats out" if emit_stats else ""), units * rows)
     rc = lib.vf_linear_proj(x.data_ptr(), wg.data_ptr(), b32.data_ptr() if b32 is not None else None, rpb,
                             residual.data_ptr() if residual is not None else None,
                             colsum.data_ptr() if colsum is not None else None, float(ln.eps) if ln is not None else 0.0,
+                            ln_stats.data_ptr() if ln_stats is not None else None, parts,
+                            stats.data_ptr() if stats is not None else None,
                             out.data_ptr(), rows, k, n, k, n, n, _code(x), _stream(x))
     _lib.check(rc, "vf_linear_proj")
     _count()
-    return out
+    return (out, stats) if emit_stats else out
 
 
 def conv3x3_out_f32(x_nhwc: torch.Tensor, conv) -> torch.Tensor:
