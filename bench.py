@@ -222,9 +222,26 @@ def run_reference_arm(args, rank):
 
 
 # ---- per-kernel rooflines of the memory-bound kernels (timed live inside steps of the bench loop) ---------------------
-def summarize_secondary(events, n_steps, pk):
+def hbm_write_ceiling_gbs(device):
+    """Pure-write bandwidth of this GPU, measured live (fill of 768 MiB, best of 5, CUDA events).  The copy peak of
+    MEASURED_PEAKS.json is half reads, half writes; a kernel that mostly WRITES (the QKV projection: 1 row-unit in, 3 out)
+    is bounded by this lower figure (profiles/r2_write_bw.txt: 3.84 TB/s against 6.56 TB/s of copy traffic)."""
+    buf = torch.empty(768 << 20, dtype=torch.uint8, device=device)
+    best = 1e9
+    for _ in range(6):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        buf.zero_()
+        b.record()
+        torch.cuda.synchronize()
+        best = min(best, a.elapsed_time(b))
+    return buf.numel() / (best * 1e-3) / 1e9
+
+
+def summarize_secondary(events, n_steps, pk, write_gbs=None):
     """{kind: [(ms, work, unit), ...]} from ops.profile_kernels -> one row per kernel kind.  `work` is the ALGORITHMIC bytes
     (or flops) of the launch as DESIGN.md section 3 defines them; fractions are of the measured peaks."""
+    import re
     rows = []
     for kind, evs in sorted(events.items()):
         ms = float(np.sum([e[0] for e in evs]))
@@ -234,8 +251,16 @@ def summarize_secondary(events, n_steps, pk):
             continue
         if unit == "B":
             ach = work / (ms * 1e-3) / 1e9
-            rows.append(dict(kernel=kind, bound="hbm", launches_per_step=len(evs) / n_steps, ms_per_step=ms / n_steps,
-                             algorithmic_bytes_per_step=work / n_steps, achieved=ach, unit="GB/s", peak=pk["hbm"], frac=ach / pk["hbm"]))
+            row = dict(kernel=kind, bound="hbm", launches_per_step=len(evs) / n_steps, ms_per_step=ms / n_steps,
+                       algorithmic_bytes_per_step=work / n_steps, achieved=ach, unit="GB/s", peak=pk["hbm"], frac=ach / pk["hbm"])
+            m = re.match(r"linear_proj k=(\d+) n=(\d+)", kind)
+            if m and write_gbs:
+                # write-heavy projection: its floor is max(all bytes at the copy peak, written bytes at the write ceiling)
+                k_, n_ = int(m.group(1)), int(m.group(2))
+                wfrac = n_ / (k_ + n_ + (n_ if "+res" in kind else 0))
+                floor_ms = max(work / pk["hbm"], work * wfrac / write_gbs) / 1e9 * 1e3
+                row.update(written_bytes_per_step=work * wfrac / n_steps, hbm_write_ceiling=write_gbs, frac_of_floor=floor_ms / ms)
+            rows.append(row)
         else:
             ach = work / (ms * 1e-3) / 1e12
             rows.append(dict(kernel=kind, bound="tensor", launches_per_step=len(evs) / n_steps, ms_per_step=ms / n_steps,
@@ -475,7 +500,7 @@ def main():
         with torch.no_grad():
             for i in range(W + K, W + K + 2):
                 x = one_step(i, x)
-        secondary = summarize_secondary(ops.profile_kernels(None), 2, peaks())
+        secondary = summarize_secondary(ops.profile_kernels(None), 2, peaks(), hbm_write_ceiling_gbs(device))
         barrier()
 
     # secondary figure ("report throughput both ways"): the same steps with the output-dead recon
