@@ -1,4 +1,4 @@
-"""One launch each of the projection kernel's two forms at the size of a 32-frame step (for ncu): LN + QKV, to_out + row + residual."""
+"""One launch each of the projection kernel's four forms at the size of a 32-frame step (for ncu): LN + QKV, to_out + row + residual."""
 import os, sys
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -14,7 +14,9 @@ bo = torch.randn(320, device="cuda", generator=g).bfloat16()
 row = torch.randn(b, 320, device="cuda", generator=g).bfloat16()
 ops._ProjFold.get(wq, None, ln); ops._ProjFold.get(wo, bo, None)
 torch.cuda.synchronize()
-ops.linear_proj(x, wq, None, None, ln=ln)
-ops.linear_proj(a, wo, bo, x, row_bias=row)
+t, st = ops.linear_proj(a, wo, bo, emit_stats=True)          # proj_in form: emits the row statistics
+ops.linear_proj(t, wq, None, None, ln=ln, ln_stats=st)        # LN + QKV with the statistics handed over
+ops.linear_proj(x, wq, None, None, ln=ln)                     # LN + QKV with in-kernel statistics
+ops.linear_proj(a, wo, bo, x, row_bias=row)                   # to_out + per-sample row + residual
 torch.cuda.synchronize()
 print("ok")
