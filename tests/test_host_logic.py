@@ -260,3 +260,46 @@ def test_library_has_no_link_time_cublas_dependency():
     needed = [ln for ln in out.splitlines() if "NEEDED" in ln]
     assert needed, out
     assert not any("cublas" in ln.lower() for ln in needed), needed
+
+
+def test_projection_fold_algebra_matches_layernorm_then_linear():
+    """ops._ProjFold (host side of vf_linear_proj): LN(x) W^T + b == rstd (x Wg^T - mean colsum(Wg)) + (beta W^T + b) with
+    Wg = bf16(W o gamma) and the column sums taken over the ROUNDED Wg -- evaluated here in fp64 on the CPU, the same
+    expression the kernel's epilogue applies (reference: ldm/modules/attention.py:239 with :172-174)."""
+    import torch
+    from vface_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    k, n, rows = 320, 960, 64
+    ln = torch.nn.LayerNorm(k).to(torch.bfloat16)
+    with torch.no_grad():
+        ln.weight.copy_((1.0 + 0.3 * torch.randn(k, generator=g)).to(torch.bfloat16))
+        ln.bias.copy_((0.2 * torch.randn(k, generator=g)).to(torch.bfloat16))
+    w = (torch.randn(n, k, generator=g) * k ** -0.5).to(torch.bfloat16)
+    b = (0.5 * torch.randn(n, generator=g)).to(torch.bfloat16)
+    x = (1.5 * torch.randn(rows, k, generator=g) + 0.7).to(torch.bfloat16)
+    wg, colsum, b32 = ops._ProjFold.get(w, b, ln)
+    assert wg.dtype == torch.bfloat16 and colsum.dtype == torch.float32 and b32.dtype == torch.float32
+    assert torch.equal(colsum, wg.float().sum(1))
+    xd = x.double()
+    mean = xd.mean(1, keepdim=True)
+    rstd = 1.0 / torch.sqrt(xd.var(1, unbiased=False, keepdim=True) + ln.eps)
+    folded = rstd * (xd @ wg.double().t() - mean * colsum.double()[None]) + b32.double()[None]
+    direct = ((xd - mean) * rstd * ln.weight.double() + ln.bias.double()) @ w.double().t() + b.double()
+    # the only difference is the bf16 rounding of W o gamma (2^-9 relative per weight, averaged over k = 320 terms)
+    assert ((folded - direct).norm() / direct.norm()).item() < 2.0 ** -9
+    # cached, and the cache entry pins its source tensors
+    assert ops._ProjFold.get(w, b, ln)[0] is wg
+    # without a LayerNorm the weight is passed through untouched and the bias only changes dtype
+    w2, cs2, b2 = ops._ProjFold.get(w, b, None)
+    assert cs2 is None and w2.data_ptr() == w.data_ptr() and torch.equal(b2, b.float())
+
+
+def test_arming_norm1_does_not_register_a_submodule():
+    """BasicTransformerBlock hands norm1 to attn1.project_qkv through a plain attribute: the module tree (state-dict keys,
+    which must stay the reference's) is unchanged while it is armed."""
+    from vface_b200.ldm.modules.attention import BasicTransformerBlock
+    blk = BasicTransformerBlock(320, 8, 40, context_dim=768)
+    keys = list(blk.state_dict().keys())
+    object.__setattr__(blk.attn1, "_pre_ln", blk.norm1)
+    assert list(blk.state_dict().keys()) == keys and "_pre_ln" not in dict(blk.attn1.named_modules())
+    object.__setattr__(blk.attn1, "_pre_ln", None)

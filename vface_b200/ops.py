@@ -526,7 +526,7 @@ class _ProjFold:
         key = tuple((p.data_ptr(), p._version, p.dtype, p.device) for p in ps) + (bias is None, ln is None)
         hit = cls._cache.get(key)
         if hit is not None:
-            return hit
+            return hit[:3]
         if len(cls._cache) > 512:
             cls._cache.clear()
         with torch.no_grad():
@@ -541,9 +541,10 @@ class _ProjFold:
                 wg = weight.detach().contiguous()
                 colsum = None
             b32 = b32.contiguous() if b32 is not None else None
-        hit = (wg, colsum, b32)
-        cls._cache[key] = hit
-        return hit
+        # the entry keeps its source tensors alive: a freed parameter's address (and version 0) could otherwise be handed to
+        # a new tensor and hit this entry with stale folded constants
+        cls._cache[key] = (wg, colsum, b32, tuple(ps))
+        return wg, colsum, b32
 
 
 def linear_proj_supported(x: torch.Tensor, weight: torch.Tensor) -> bool:
