@@ -164,6 +164,37 @@ def attention(q: np.ndarray, k: np.ndarray, v: np.ndarray, heads: int, scale: fl
             out[bi, :, sl] = p @ v[bi, :, sl]
     return out.astype(F32)
 
+# ----------------------------------------------------------------------------------------------
+# projections of a transformer block (what csrc/vf_gemm3.cu fuses)
+# ----------------------------------------------------------------------------------------------
+def layer_norm(x: np.ndarray, gamma: np.ndarray, beta: np.ndarray, eps: float = 1e-5) -> np.ndarray:
+    """nn.LayerNorm over the last axis (ldm/modules/attention.py:233-235: norm1 / norm2 / norm3;
+    biased variance, eps inside the square root).  float64 arithmetic."""
+    xd = x.astype(np.float64)
+    mu = xd.mean(-1, keepdims=True)
+    var = ((xd - mu) ** 2).mean(-1, keepdims=True)
+    return (xd - mu) / np.sqrt(var + eps) * gamma.astype(np.float64) + beta.astype(np.float64)
+
+
+def block_projection(x, w, bias=None, residual=None, ln=None, row_bias=None) -> np.ndarray:
+    """One projection of a BasicTransformerBlock / SpatialTransformer with what surrounds it in the reference:
+
+        y = Linear(LayerNorm(x)) + residual + row_bias[sample]
+
+    ln = (gamma, beta, eps) or None.  Restates `self.attn1(self.norm1(x))`'s norm + to_q / to_k / to_v
+    (attention.py:239, :172-174, with w = [Wq; Wk; Wv]), `to_out(...) + x` and the attn2 row of a single-token context
+    (attention.py:176, :239-241), proj_in and `proj_out(x) + x_in` as 1x1 convolutions over tokens (attention.py:261-288).
+    x (..., k), w (n, k), bias (n), residual (..., n), row_bias (batch, n) for x (batch, tokens, k).  float64."""
+    xd = layer_norm(x, *ln) if ln is not None else x.astype(np.float64)
+    y = xd @ w.astype(np.float64).T
+    if bias is not None:
+        y = y + bias.astype(np.float64)
+    if row_bias is not None:
+        y = y + row_bias.astype(np.float64)[:, None, :]
+    if residual is not None:
+        y = y + residual.astype(np.float64)
+    return y
+
 
 # ----------------------------------------------------------------------------------------------
 # CFG + DDIM update

@@ -421,11 +421,56 @@ def golden_vae_encoder():
          keys=np.array(sorted(sd.keys())))
 
 
+def block_projection_inputs(seed=77, batch=2, tokens=128, dim=320, ctx_dim=768):
+    """Seeded inputs and parameters of golden_block_projection (regenerated by the tests: same torch build here and on
+    the GPU box).  Parameters are rounded to bf16-representable values so that the bf16 CUDA path sees the same numbers."""
+    g = torch.Generator().manual_seed(seed)
+    r = lambda *s, scale=1.0, shift=0.0: (torch.randn(*s, generator=g) * scale + shift).bfloat16().float()
+    return dict(
+        x=r(batch, tokens, dim, scale=1.3, shift=0.2), a=r(batch, tokens, dim), ctx=r(batch, 1, ctx_dim),
+        g_in=r(batch, tokens, dim), t_out=r(batch, tokens, dim),
+        n1_w=r(dim, scale=0.3, shift=1.0), n1_b=r(dim, scale=0.2),
+        wq=r(dim, dim, scale=dim ** -0.5), wk=r(dim, dim, scale=dim ** -0.5), wv=r(dim, dim, scale=dim ** -0.5),
+        wo1=r(dim, dim, scale=dim ** -0.5), bo1=r(dim, scale=0.3),
+        wv2=r(dim, ctx_dim, scale=ctx_dim ** -0.5), wo2=r(dim, dim, scale=dim ** -0.5), bo2=r(dim, scale=0.3),
+        w_in=r(dim, dim, scale=dim ** -0.5), b_in=r(dim, scale=0.3), w_out=r(dim, dim, scale=dim ** -0.5), b_out=r(dim, scale=0.3))
+
+
+def golden_block_projection():
+    """What the tcgen05 projection kernel (csrc/vf_gemm3.cu) replaces, computed by the reference's own modules
+    (ldm/modules/attention.py: BasicTransformerBlock :224-243, CrossAttention :152-221, SpatialTransformer :246-288):
+    norm1 + to_q/to_k/to_v; to_out(a) + x followed by attn2(norm2(.), single-token ctx) + .; proj_in; proj_out + x_in."""
+    from ldm.modules.attention import BasicTransformerBlock, SpatialTransformer
+    d = block_projection_inputs()
+    dim = d["x"].shape[-1]
+    with quiet():
+        blk = BasicTransformerBlock(dim, 8, dim // 8, context_dim=d["ctx"].shape[-1]).eval()
+        st = SpatialTransformer(dim, 8, dim // 8, depth=1, context_dim=d["ctx"].shape[-1]).eval()
+    with torch.no_grad():
+        blk.norm1.weight.copy_(d["n1_w"]); blk.norm1.bias.copy_(d["n1_b"])
+        blk.attn1.to_q.weight.copy_(d["wq"]); blk.attn1.to_k.weight.copy_(d["wk"]); blk.attn1.to_v.weight.copy_(d["wv"])
+        blk.attn1.to_out[0].weight.copy_(d["wo1"]); blk.attn1.to_out[0].bias.copy_(d["bo1"])
+        blk.attn2.to_v.weight.copy_(d["wv2"]); blk.attn2.to_out[0].weight.copy_(d["wo2"]); blk.attn2.to_out[0].bias.copy_(d["bo2"])
+        st.proj_in.weight.copy_(d["w_in"][:, :, None, None]); st.proj_in.bias.copy_(d["b_in"])
+        st.proj_out.weight.copy_(d["w_out"][:, :, None, None]); st.proj_out.bias.copy_(d["b_out"])
+        n1 = blk.norm1(d["x"])
+        qkv = torch.cat([blk.attn1.to_q(n1), blk.attn1.to_k(n1), blk.attn1.to_v(n1)], dim=-1)
+        x1 = blk.attn1.to_out(d["a"]) + d["x"]                                  # attention.py:239 with a = the attention output
+        x2 = blk.attn2(blk.norm2(x1), context=d["ctx"]) + x1                    # attention.py:240-241, single-token context
+        b, n, c = d["g_in"].shape
+        hh, ww = 8, n // 8
+        nchw = lambda t: t.reshape(b, hh, ww, c).permute(0, 3, 1, 2).contiguous()
+        tok = lambda t: t.permute(0, 2, 3, 1).reshape(b, n, c)
+        p_in = tok(st.proj_in(nchw(d["g_in"])))                                 # attention.py:279
+        p_out = tok(st.proj_out(nchw(d["t_out"])) + nchw(d["x"]))               # attention.py:287-288
+    save("block_projection.npz", qkv=qkv.numpy(), x2=x2.numpy(), proj_in=p_in.numpy(), proj_out=p_out.numpy())
+
+
 def main():
     if not rh.available():
         sys.exit("reference not mounted; golden vectors can only be generated in the build container")
     rh.install()
-    which = sys.argv[1:] or ["fsai", "warp", "attn_hooks", "schedule", "sampler_small", "unet_full", "sampler_full", "sampler_full_s10", "sampler_full_8f", "sampler_small_2way", "sampler_small_eta", "vae_decoder", "vae_decoder_full", "vae_encoder"]
+    which = sys.argv[1:] or ["fsai", "warp", "attn_hooks", "schedule", "sampler_small", "unet_full", "sampler_full", "sampler_full_s10", "sampler_full_8f", "sampler_small_2way", "sampler_small_eta", "vae_decoder", "vae_decoder_full", "vae_encoder", "block_projection"]
     for w in which:
         globals()["golden_" + w]()
 

@@ -173,3 +173,36 @@ def test_linear_proj_full_size_matches_library_path():
     d2 = got2.float() - want2.float()
     assert (d2.norm() / want2.float().norm()).item() < 4 * 2.0 ** -9
     assert d2.abs().max().item() < BF16_TOL * max(1.0, want2.float().abs().max().item() / 2.0)
+
+
+def test_linear_proj_vs_reference_golden():
+    """The four uses of the kernel against outputs of the reference's own modules (tests/golden/block_projection.npz:
+    BasicTransformerBlock.norm1 + attn1.to_q/k/v, attn1.to_out + x + single-token attn2, SpatialTransformer.proj_in and
+    proj_out + x_in, computed by the unmodified reference in fp32).  bf16 tolerance 2e-2 on O(1..4) values."""
+    import os
+    import numpy as np
+    from oracle.make_golden import block_projection_inputs
+    from vface_b200 import ops
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "block_projection.npz"))
+    d = {k: v.to(_dev()).bfloat16() for k, v in block_projection_inputs().items()}      # all values are bf16-representable
+    ln = torch.nn.LayerNorm(320).to(_dev()).bfloat16()
+    with torch.no_grad():
+        ln.weight.copy_(d["n1_w"])
+        ln.bias.copy_(d["n1_b"])
+
+    def close(got, name):
+        want = torch.from_numpy(g[name]).to(_dev())
+        err = (got.float() - want).abs().max().item()
+        assert err < BF16_TOL * max(1.0, want.abs().max().item() / 2.0), (name, err)
+        assert ((got.float() - want).norm() / want.norm()).item() < 3 * 2.0 ** -9, name
+
+    wqkv = torch.cat([d["wq"], d["wk"], d["wv"]], 0).contiguous()
+    close(ops.linear_proj(d["x"], wqkv, ln=ln), "qkv")
+    t, st = ops.linear_proj(d["g_in"], d["w_in"], d["b_in"], emit_stats=True)
+    close(t, "proj_in")
+    row = torch.nn.functional.linear(torch.nn.functional.linear(d["ctx"][:, 0], d["wv2"]), d["wo2"], d["bo2"])
+    close(ops.linear_proj(d["a"], d["wo1"], d["bo1"], d["x"], row_bias=row), "x2")
+    close(ops.linear_proj(d["t_out"], d["w_out"], d["b_out"], d["x"]), "proj_out")
+    # and the hand-over: statistics emitted for g_in's projection drive the LayerNorm of a projection of that output
+    q2 = ops.linear_proj(t, wqkv, ln=ln, ln_stats=st)
+    assert (q2.float() - ops.linear_proj(t, wqkv, ln=ln).float()).abs().max().item() < BF16_TOL
