@@ -1124,6 +1124,306 @@ static int gn_resident_launch(GnParams& P, int tpr, int rpb, int threads, cudaSt
   return gn_resident_launch_t<T, 2>(P, tpr, rpb, threads, st);
 }
 
+// ---- resident GroupNorm, two slabs per CTA in flight (third session of round 2) ---------------------------------
+// gn_resident_kernel runs the phases of an item strictly in sequence -- load, statistics, publish, WAIT for the rest of the
+// sample, totals, apply -- and its CTA moves no data while it waits: 23 % of all warp-stall samples sit on the barrier behind
+// thread 0's poll of the sample counter, another 10 % on the slab's own load (ncu source view of profiles/r2_gn_resident_ncu.txt).
+// Here a CTA holds TWO half-size slabs: the FRONT half of an item (issue the bulk copies, statistics as they land, publish the
+// partials, arrive on the sample counter) never blocks on another CTA, so the front of item i+1 is run BEFORE the BACK half of
+// item i (wait for the sample, totals, apply out of shared memory): the wait of item i and the load of item i+1 overlap, and
+// the copies of item i+2 are in flight under the apply pass of item i+1.  MEASURED SLOWER than the one-slab kernel (see the
+// dispatch below); kept as an opt-in (VF_GN_PIPE=1).  Deadlock-free for the same reason as before: every
+// ticket a CTA holds is published before that CTA waits for anything (tickets are handed out in sample-major order, so every
+// slab of an awaited sample is held by a running CTA that will publish it without waiting).
+struct Gnr2Header {
+  uint64_t bar[2][kGnrChunks];
+  float mean[kGnMaxGroups], rstd[kGnMaxGroups];
+  int item;
+};
+static_assert(sizeof(Gnr2Header) <= kGnrHeaderBytes, "header");
+
+template <typename T, int kMinB>
+__global__ void __launch_bounds__(kGnfMaxThreads, kMinB)
+gn_resident2_kernel(const GnParams P, const int tpr, const int rpb, const int set) {
+  constexpr int E = V16<T>::E;
+  extern __shared__ __align__(128) unsigned char gnr_smem[];
+  Gnr2Header* H = reinterpret_cast<Gnr2Header*>(gnr_smem);
+  float4* s_pair = reinterpret_cast<float4*>(gnr_smem + kGnrHeaderBytes);          // per thread: (sum, sq) of its two groups
+  T* buf0 = reinterpret_cast<T*>(gnr_smem + kGnrHeaderBytes + kGnrMaxThreads * sizeof(float4));
+  unsigned int* sync = g_gn_sync[set & 0xff];
+  const int tid = threadIdx.x;
+  const int my_row = tid / tpr, my_chunk = tid - my_row * tpr;
+  const bool active = my_row < rpb;
+  const int ch = my_chunk * E;
+  const int cpg = P.c / P.groups;                       // >= E: a 16-byte chunk touches at most two groups
+  const int c1 = P.c1, c2 = P.c - P.c1;
+  const int total = P.n * P.slabs;
+  const size_t buf_elems = (size_t)P.rows_per_slab * P.c;
+  const bool from1 = ch < c1;
+  const int ld = from1 ? c1 : c2;
+  const size_t my_off = from1 ? (size_t)ch : (size_t)P.rows_per_slab * c1 + (ch - c1);     // within a buffer: slab1 | slab2
+  const int g_lo = ch / cpg;
+  const int n_lo = min(E, (g_lo + 1) * cpg - ch);       // channels of the chunk that belong to g_lo
+
+  if (tid == 0) {
+    for (int b = 0; b < 2; ++b)
+      for (int k = 0; k < kGnrChunks; ++k) sm100::mbar_init(&H->bar[b][k], 1);
+    sm100::fence_barrier_init();
+  }
+
+  // next ticket, broadcast to the CTA.  The barrier also orders every thread's reads of a buffer (apply pass) before
+  // thread 0 hands that buffer to the next bulk copies.
+  auto take = [&]() -> int {
+    if (tid == 0) H->item = (int)atomicAdd(&sync[0], 1u);
+    __syncthreads();
+    const int it = H->item;
+    __syncthreads();                                    // H->item may be rewritten by the next take()
+    return it;
+  };
+
+  // ---- front half: loads, statistics, publish, arrive.  Never waits for another CTA. ---------------------------------
+  auto front = [&](const int item, const int b, const uint32_t phase, float (&av)[E]) {
+    const int n = item / P.slabs, slab = item - n * P.slabs;
+    const int r0 = slab * P.rows_per_slab;
+    const int nrows = min(P.hw, r0 + P.rows_per_slab) - r0;
+    int rows_per_chunk = (nrows + kGnrChunks - 1) / kGnrChunks;
+    rows_per_chunk = (rows_per_chunk + rpb - 1) / rpb * rpb;        // a thread's rows do not depend on the chunking
+    T* slab1 = buf0 + (size_t)b * buf_elems;
+    T* slab2 = slab1 + (size_t)P.rows_per_slab * c1;
+    if (tid == 0) {
+      const T* g1 = reinterpret_cast<const T*>(P.x) + ((size_t)n * P.hw + r0) * c1;
+      const T* g2 = c2 ? reinterpret_cast<const T*>(P.x2) + ((size_t)n * P.hw + r0) * c2 : nullptr;
+      for (int k = 0; k < kGnrChunks; ++k) {
+        const int a = min(nrows, k * rows_per_chunk), e = min(nrows, (k + 1) * rows_per_chunk);
+        const uint32_t b1 = (uint32_t)((size_t)(e - a) * c1 * sizeof(T));
+        const uint32_t b2 = c2 ? (uint32_t)((size_t)(e - a) * c2 * sizeof(T)) : 0u;
+        sm100::mbar_arrive_expect_tx(&H->bar[b][k], b1 + b2);          // 0 bytes: completes at once
+        if (b1) bulk_g2s(slab1 + (size_t)a * c1, g1 + (size_t)a * c1, b1, &H->bar[b][k]);
+        if (b2) bulk_g2s(slab2 + (size_t)a * c2, g2 + (size_t)a * c2, b2, &H->bar[b][k]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < E; ++j) av[j] = 0.f;
+    if (active && P.add_nc) V16<T>::ld(reinterpret_cast<const T*>(P.add_nc) + (size_t)n * P.c + ch, av);
+    const T* my_slab = slab1 + my_off;
+    {
+      float sum[E], sq[E];
+      {
+        float2 sum2[E / 2], sq2[E / 2];
+#pragma unroll
+        for (int j = 0; j < E / 2; ++j) { sum2[j] = make_float2(0.f, 0.f); sq2[j] = make_float2(0.f, 0.f); }
+        int r = my_row;
+        for (int kc = 0; kc < kGnrChunks; ++kc) {
+          sm100::mbar_wait(&H->bar[b][kc], phase);
+          const int e = min(nrows, (kc + 1) * rows_per_chunk);
+          if (active) {
+#pragma unroll 4
+            for (; r < e; r += rpb) {
+              float2 v[E / 2];
+              P16<T>::unpack(*reinterpret_cast<const uint4*>(my_slab + (size_t)r * ld), v);
+#pragma unroll
+              for (int j = 0; j < E / 2; ++j) { sum2[j] = __fadd2_rn(sum2[j], v[j]); sq2[j] = __ffma2_rn(v[j], v[j], sq2[j]); }
+            }
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < E / 2; ++j) {
+          sum[2 * j] = sum2[j].x; sum[2 * j + 1] = sum2[j].y;
+          sq[2 * j] = sq2[j].x; sq[2 * j + 1] = sq2[j].y;
+        }
+      }
+      if (active) {
+        if (P.add_nc) {                                   // sum(x + a) = sum(x) + N a, sum((x + a)^2) = sum(x^2) + a (2 sum(x) + N a)
+          const float cnt = (float)(my_row < nrows ? (nrows - my_row + rpb - 1) / rpb : 0);
+#pragma unroll
+          for (int j = 0; j < E; ++j) {
+            sq[j] = fmaf(av[j], fmaf(cnt, av[j], 2.0f * sum[j]), sq[j]);
+            sum[j] = fmaf(cnt, av[j], sum[j]);
+          }
+        }
+        float4 pr = make_float4(0.f, 0.f, 0.f, 0.f);      // (sum, sq) of g_lo, (sum, sq) of g_lo + 1
+#pragma unroll
+        for (int j = 0; j < E; ++j) {
+          if (j < n_lo) { pr.x += sum[j]; pr.y += sq[j]; }
+          else { pr.z += sum[j]; pr.w += sq[j]; }
+        }
+        s_pair[tid] = pr;
+      }
+    }
+    __syncthreads();
+    // group totals of the slab: eight lanes per group over (row lane, chunk) in a fixed order, then a fixed tree
+    for (int grp = tid >> 3; grp < P.groups; grp += blockDim.x >> 3) {
+      const int sub = tid & 7;
+      const int k0 = (grp * cpg) / E, k1 = ((grp + 1) * cpg - 1) / E;       // chunks that touch the group
+      const int nk = k1 - k0 + 1;
+      float gs = 0.f, gq = 0.f;
+      for (int i = sub; i < nk * rpb; i += 8) {
+        const int rr = i / nk, k = k0 + (i - rr * nk);
+        const float4 pr = s_pair[rr * tpr + k];
+        const bool lo = (k * E) / cpg == grp;
+        gs += lo ? pr.x : pr.z;
+        gq += lo ? pr.y : pr.w;
+      }
+      const unsigned m8 = 0xffu << (tid & 24);
+#pragma unroll
+      for (int o = 4; o > 0; o >>= 1) {
+        gs += __shfl_xor_sync(m8, gs, o);
+        gq += __shfl_xor_sync(m8, gq, o);
+      }
+      if (sub == 0) {
+        float* w = P.ws + (((size_t)n * P.slabs + slab) * P.groups + grp) * 2;
+        __stcg(w, gs);
+        __stcg(w + 1, gq);
+      }
+    }
+    __syncthreads();
+    if (tid == 0) {
+      // release: the CTA's partials (ordered before this thread by the barrier) become visible with the arrival
+      unsigned seen;
+      asm volatile("atom.add.release.gpu.global.u32 %0, [%1], 1;" : "=r"(seen) : "l"(&sync[2 + 2 * n]) : "memory");
+      (void)seen;
+    }
+  };
+
+  // ---- back half: wait for the sample, totals, apply out of shared memory ----------------------------------------------
+  auto back = [&](const int item, const int b, const float (&av)[E]) {
+    const int n = item / P.slabs, slab = item - n * P.slabs;
+    const int r0 = slab * P.rows_per_slab;
+    const int nrows = min(P.hw, r0 + P.rows_per_slab) - r0;
+    const T* my_slab = buf0 + (size_t)b * buf_elems + my_off;
+    if (tid == 0) {
+      if (!(set & 0x100))                                 // 0x100: VF_GN_DEBUG_NOWAIT (timing experiment, wrong results)
+        while (ld_acquire_u32(&sync[2 + 2 * n]) < (unsigned)P.slabs) __nanosleep(32);
+      asm volatile("fence.acq_rel.gpu;" ::: "memory");
+    }
+    __syncthreads();
+    // totals of the sample: eight lanes per group, slabs strided over the lanes, then a fixed shuffle tree in double -- the
+    // same order in every CTA of the sample
+    if (tid < 8 * P.groups) {
+      const int grp = tid >> 3, sub = tid & 7;
+      double sd = 0.0, qd = 0.0;
+      const float2* w = reinterpret_cast<const float2*>(P.ws) + ((size_t)n * P.slabs) * P.groups + grp;
+      for (int i0 = sub; i0 < P.slabs; i0 += 32) {
+        float2 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int i = i0 + 8 * u;
+          v[u] = i < P.slabs ? __ldcg(w + (size_t)i * P.groups) : make_float2(0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { sd += (double)v[u].x; qd += (double)v[u].y; }
+      }
+      const unsigned m8 = 0xffu << (tid & 24);
+#pragma unroll
+      for (int o = 4; o > 0; o >>= 1) {
+        sd += __shfl_xor_sync(m8, sd, o);
+        qd += __shfl_xor_sync(m8, qd, o);
+      }
+      if (sub == 0) {
+        const double cnt = (double)P.hw * cpg;
+        const double mean = sd / cnt;
+        double var = qd / cnt - mean * mean;
+        if (var < 0.0) var = 0.0;
+        H->mean[grp] = (float)mean;
+        H->rstd[grp] = (float)(1.0 / sqrt(var + (double)P.eps));
+      }
+    }
+    __syncthreads();
+    if (active) {
+      float scale[E], shift[E], gam[E], bet[E];          // gamma / beta: the same lines every item, L1 hits
+      V16<T>::ld(reinterpret_cast<const T*>(P.gamma) + ch, gam);
+      V16<T>::ld(reinterpret_cast<const T*>(P.beta) + ch, bet);
+#pragma unroll
+      for (int j = 0; j < E; ++j) {
+        const int grp = (ch + j) / cpg;
+        scale[j] = H->rstd[grp] * gam[j];
+        shift[j] = fmaf(av[j] - H->mean[grp], scale[j], bet[j]);
+      }
+      // bf16 SiLU = h + h tanh(h), h = t / 2: the 1/2 is folded into scale / shift, the rest is two packed FMAs per pair
+      constexpr bool kBf = sizeof(T) == 2;
+      const float ks = (kBf && P.silu) ? 0.5f : 1.0f;
+      float2 scale2[E / 2], shift2[E / 2];
+#pragma unroll
+      for (int j = 0; j < E / 2; ++j) {
+        scale2[j] = make_float2(scale[2 * j] * ks, scale[2 * j + 1] * ks);
+        shift2[j] = make_float2(shift[2 * j] * ks, shift[2 * j + 1] * ks);
+      }
+      char* q = reinterpret_cast<char*>(reinterpret_cast<T*>(P.y) + ((size_t)n * P.hw + r0 + my_row) * P.c + ch);
+      const size_t qstride = (size_t)rpb * P.c * sizeof(T);
+#pragma unroll 4
+      for (int r = my_row; r < nrows; r += rpb, q += qstride) {
+        float2 v[E / 2];
+        P16<T>::unpack(*reinterpret_cast<const uint4*>(my_slab + (size_t)r * ld), v);
+#pragma unroll
+        for (int j = 0; j < E / 2; ++j) {
+          float2 t = __ffma2_rn(v[j], scale2[j], shift2[j]);
+          if (P.silu) {
+            if constexpr (kBf) {
+              float2 th;
+              asm("tanh.approx.f32 %0, %1;" : "=f"(th.x) : "f"(t.x));
+              asm("tanh.approx.f32 %0, %1;" : "=f"(th.y) : "f"(t.y));
+              t = __ffma2_rn(t, th, t);
+            } else {
+              t = make_float2(silu_f<T>(t.x), silu_f<T>(t.y));
+            }
+          }
+          v[j] = t;
+        }
+        st_na_v4(q, P16<T>::pack(v));
+      }
+    }
+  };
+
+  float av_a[E], av_b[E];
+  uint32_t ph_a = 0, ph_b = 0;
+  __syncthreads();                                      // barrier initialisation visible
+  int it_a = take();
+  if (it_a < total) {
+    front(it_a, 0, ph_a, av_a); ph_a ^= 1u;
+    for (;;) {
+      const int it_b = take();
+      if (it_b < total) { front(it_b, 1, ph_b, av_b); ph_b ^= 1u; }
+      back(it_a, 0, av_a);
+      if (it_b >= total) break;
+      it_a = take();
+      if (it_a < total) { front(it_a, 0, ph_a, av_a); ph_a ^= 1u; }
+      back(it_b, 1, av_b);
+      if (it_a >= total) break;
+    }
+  }
+  // the last CTA out re-arms the set: ticket, exit count and the arrival counters of all samples (every CTA has
+  // left its loop by then, nobody reads them any more)
+  __syncthreads();
+  if (tid == 0) {
+    __threadfence();
+    H->item = (int)atomicAdd(&sync[1], 1u);
+  }
+  __syncthreads();
+  if (H->item == (int)gridDim.x - 1) {
+    for (int i = tid; i < P.n; i += blockDim.x) sync[2 + 2 * i] = 0u;
+    if (tid == 0) { sync[0] = 0u; sync[1] = 0u; }
+  }
+}
+
+template <typename T>
+static int gn_resident2_launch(GnParams& P, int tpr, int rpb, int threads, cudaStream_t st) {
+  static unsigned launch_no2 = 0;
+  const int set = (int)(launch_no2++ % kGnSyncSets);
+  const size_t smem = kGnrHeaderBytes + kGnrMaxThreads * sizeof(float4) + 2 * (size_t)P.rows_per_slab * P.c * sizeof(T);
+  static bool attr = false;
+  if (!attr) {
+    VF_CUDA_TRY(cudaFuncSetAttribute(gn_resident2_kernel<T, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gnr_smem_per_cta()));
+    attr = true;
+  }
+  long long grid = (long long)P.n * P.slabs;
+  const long long cap = 2LL * num_sms();
+  if (grid > cap) grid = cap;
+  static int nowait = -1;
+  if (nowait < 0) { const char* e_ = getenv("VF_GN_DEBUG_NOWAIT"); nowait = e_ ? atoi(e_) : 0; }
+  gn_resident2_kernel<T, 2><<<(int)grid, threads, smem, st>>>(P, tpr, rpb, set | (nowait ? 0x100 : 0));
+  return check_cuda(cudaGetLastError(), "gn_resident2_kernel launch");
+}
+
 // ================================================================================================
 // residual add + bias + LayerNorm (one warp per row)
 // ================================================================================================
@@ -1547,6 +1847,18 @@ extern "C" int vf_group_norm_nhwc_cat(const void* x, int c1, const void* x2, int
         const int rpb_r = mt / tpr;
         const int threads_r = (tpr * rpb_r + 31) / 32 * 32;
         const size_t budget = gnr_smem_per_cta() - kGnrHeaderBytes - kGnrMaxThreads * sizeof(float4);
+        // VF_GN_PIPE=1 (opt-in): two half-size slabs per CTA, the front half of the next item ahead of the wait of the
+        // current one (gn_resident2_kernel).  Correct, and SLOWER (0.180 vs 0.133 ms at 96 x 4096 x 320; the same with the
+        // wait skipped): what an item costs is its fixed chain of block barriers, reductions and L2 round trips, and half-size
+        // slabs pay it twice as often (profiles/r2_gn_pipe_ab.txt).  Default 0: one ~100 KB slab per CTA.
+        static int pipe = -1;
+        if (pipe < 0) { const char* e_ = getenv("VF_GN_PIPE"); pipe = e_ ? atoi(e_) : 0; }
+        if (pipe) {
+          gnr_plan(n, hw, c, dtype == VF_F32 ? 4 : 2, rpb_r, budget / 2, &P.slabs, &P.rows_per_slab);
+          if (P.slabs > 0 && (long long)n * P.slabs >= 4LL * num_sms())
+            return dtype == VF_F32 ? gn_resident2_launch<float>(P, tpr, rpb_r, threads_r, st)
+                                   : gn_resident2_launch<__nv_bfloat16>(P, tpr, rpb_r, threads_r, st);
+        }
         gnr_plan(n, hw, c, dtype == VF_F32 ? 4 : 2, rpb_r, budget, &P.slabs, &P.rows_per_slab);
         if (P.slabs > 0)
           return dtype == VF_F32 ? gn_resident_launch<float>(P, tpr, rpb_r, threads_r, st)
