@@ -150,3 +150,39 @@ def test_geglu_and_add_bias(dtype, tol):
     inplace = x.clone()
     ops.add_bias(inplace, None, vec, out=inplace)
     assert (inplace.float() - (x.float() + vec.float())).abs().max().item() < tol * 4
+
+
+def test_group_norm_two_slab_pipeline_env_knob():
+    """VF_GN_PIPE=1 (opt-in, read once per process): the resident GroupNorm with two half-size slabs per CTA in flight
+    (vf_norm.cu: gn_resident2_kernel).  Same op, same bound: fp32 F.group_norm (+ SiLU) on the bf16 inputs, including the
+    never-materialised concatenation, the additive vector and a batch small enough to fall back to the one-slab kernel;
+    run twice to check that the counters were re-armed and that the result is bit-reproducible."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = r'''
+import torch, torch.nn.functional as F
+from vface_b200 import ops
+dev = torch.device("cuda:0")
+g = torch.Generator().manual_seed(5)
+for n, hw, c1, c2, add in ((96, 4096, 320, 0, True), (96, 1024, 640, 320, False), (24, 256, 1280, 0, True), (3, 4096, 320, 0, False)):
+    c = c1 + c2
+    x1 = (torch.randn(n, hw, c1, generator=g) * 1.5 + 0.3).bfloat16().to(dev)
+    x2 = torch.randn(n, hw, c2, generator=g).bfloat16().to(dev) if c2 else None
+    w, b = torch.randn(c, generator=g).bfloat16().to(dev), torch.randn(c, generator=g).bfloat16().to(dev)
+    a = torch.randn(n, c, generator=g).bfloat16().to(dev) if add else None
+    got = ops.group_norm_nhwc(x1, w, b, 1e-5, 32, silu=True, add_nc=a, x2=x2)
+    again = ops.group_norm_nhwc(x1, w, b, 1e-5, 32, silu=True, add_nc=a, x2=x2)
+    assert torch.equal(got, again)
+    xf = x1.float() if x2 is None else torch.cat([x1.float(), x2.float()], -1)
+    if a is not None:
+        xf = xf + a.float()[:, None, :]
+    want = F.silu(F.group_norm(xf.permute(0, 2, 1), 32, w.float(), b.float(), 1e-5).permute(0, 2, 1))
+    err = (got.float() - want).abs().max().item()
+    assert err < 2e-2 * max(1.0, want.abs().max().item() / 2.0), (n, hw, c1, c2, err)
+print("GN_PIPE_OK")
+'''
+    env = dict(os.environ, VF_GN_PIPE="1")
+    res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300, cwd=root)
+    assert res.returncode == 0 and "GN_PIPE_OK" in res.stdout, res.stdout[-2000:] + res.stderr[-2000:]
