@@ -152,9 +152,10 @@ def test_geglu_and_add_bias(dtype, tol):
     assert (inplace.float() - (x.float() + vec.float())).abs().max().item() < tol * 4
 
 
-def test_group_norm_two_slab_pipeline_env_knob():
-    """VF_GN_PIPE=1 (opt-in, read once per process): the resident GroupNorm with two half-size slabs per CTA in flight
-    (vf_norm.cu: gn_resident2_kernel).  Same op, same bound: fp32 F.group_norm (+ SiLU) on the bf16 inputs, including the
+@pytest.mark.parametrize("knob", ["VF_GN_PIPE", "VF_GN_WS"])
+def test_group_norm_two_slab_pipeline_env_knob(knob):
+    """VF_GN_PIPE=1 / VF_GN_WS=1 (read once per process): the resident GroupNorm with two half-size slabs per CTA in flight
+    (vf_norm.cu: gn_resident2_kernel) and its warp-specialised form (gn_ws_kernel: producer / statistics / apply warps).  Same op, same bound: fp32 F.group_norm (+ SiLU) on the bf16 inputs, including the
     never-materialised concatenation, the additive vector and a batch small enough to fall back to the one-slab kernel;
     run twice to check that the counters were re-armed and that the result is bit-reproducible."""
     import os
@@ -183,6 +184,6 @@ for n, hw, c1, c2, add in ((96, 4096, 320, 0, True), (96, 1024, 640, 320, False)
     assert err < 2e-2 * max(1.0, want.abs().max().item() / 2.0), (n, hw, c1, c2, err)
 print("GN_PIPE_OK")
 '''
-    env = dict(os.environ, VF_GN_PIPE="1")
+    env = dict(os.environ, **{knob: "1"})
     res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300, cwd=root)
     assert res.returncode == 0 and "GN_PIPE_OK" in res.stdout, res.stdout[-2000:] + res.stderr[-2000:]

@@ -1424,6 +1424,348 @@ static int gn_resident2_launch(GnParams& P, int tpr, int rpb, int threads, cudaS
   return check_cuda(cudaGetLastError(), "gn_resident2_kernel launch");
 }
 
+// ---- resident GroupNorm, warp-specialised (bf16; third session of round 2) ----------------------------------------
+// The one-slab kernel runs an item's phases in sequence on ALL its warps, with seven block barriers and a chain that ONE thread
+// walks (atomic arrival, poll, fence, ticket) while the others park; two slabs per CTA did not help because that fixed cost is
+// paid per item (gn_resident2_kernel).  Here the phases are ROLES, each with its own warps, meeting only on mbarriers:
+//   warp 0        producer: waits for a free buffer, THEN takes a ticket (a held ticket is always loadable at once), issues the
+//                 bulk copies of the slab into a ring of three 66 KB buffers;
+//   warps 1-8     statistics: per-thread sums out of shared memory, slab totals in a fixed order, partials to L2, release-arrive
+//                 on the sample counter.  This group never waits for another CTA.  (A first version let the LAST arrival of a
+//                 sample reduce the partials once and raise a ready flag: arrival -> reduce -> flag -> poll -> read is five L2
+//                 round trips on every item's critical path, 0.177 ms against 0.125 with the waits skipped.)
+//   warps 9-24    apply, two groups of eight warps taking alternate items (one group is latency-bound: 2.7 us per 66 KB slab
+//                 against 3 us of HBM time): wait until the sample's arrival counter is full (one thread polls), sum its partials
+//                 (eight lanes per group, one L2 round trip), normalise (+ SiLU) out of shared memory, store, hand the buffer back.
+// One CTA per SM; the copies of item i+2 are in flight while item i+1 is summed and item i is applied.  Deadlock-free: a ticket
+// is taken only when its buffer is free, so every held ticket is published without waiting on anyone; 3 x grid tickets in
+// flight always cover the oldest awaited sample (<= 128 slabs).  Bit-reproducible: fixed orders everywhere, and the totals of a
+// sample are computed exactly once.
+constexpr int kGwsBufs = 3;
+constexpr int kGwsGroup = 256;                          // threads of the statistics group and of the apply group
+constexpr int kGwsApplyGroups = 2;                      // apply groups taking alternate items (the apply pass is latency-bound at 8 warps)
+constexpr int kGwsThreads = 32 + (1 + kGwsApplyGroups) * kGwsGroup;
+constexpr size_t kGwsBufBytes = 66 * 1024;
+constexpr int kGwsSlabStride = 128;                     // workspace: [n][<= 128 slabs][groups][2] partials, then [n][groups][2] totals
+
+struct GwsHeader {
+  uint64_t full[kGwsBufs], stats_done[kGwsBufs], empty[kGwsBufs];
+  int item[kGwsBufs];
+  float2 mr[2][kGnMaxGroups];                           // per apply group: (mean, rstd) of the sample being applied
+};
+static_assert(sizeof(GwsHeader) <= 1024, "header");
+
+__device__ __forceinline__ void gws_bar(int id) { asm volatile("bar.sync %0, %1;" :: "r"(id), "n"(kGwsGroup) : "memory"); }
+
+__global__ void __launch_bounds__(kGwsThreads, 1)
+gn_ws_kernel(const GnParams P, const int tpr, const int rpb, const int set) {
+  using T = __nv_bfloat16;
+  constexpr int E = 8;
+  extern __shared__ __align__(128) unsigned char gws_smem[];
+  GwsHeader* H = reinterpret_cast<GwsHeader*>(gws_smem);
+  float4* s_pair = reinterpret_cast<float4*>(gws_smem + 1024);
+  unsigned char* bufs = gws_smem + 1024 + kGwsGroup * sizeof(float4);
+  unsigned int* sync = g_gn_sync[set & 0xff];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c1 = P.c1, c2 = P.c - P.c1;
+  const int cpg = P.c / P.groups;
+  const int total = P.n * P.slabs;
+
+  if (threadIdx.x == 0) {
+    for (int b = 0; b < kGwsBufs; ++b) {
+      sm100::mbar_init(&H->full[b], 1);
+      sm100::mbar_init(&H->stats_done[b], 1);
+      sm100::mbar_init(&H->empty[b], 1);
+    }
+    sm100::fence_barrier_init();
+  }
+  __syncthreads();
+
+  if (warp == 0) {
+    // =========================== producer ================================================================
+    if (lane == 0) {
+      int ends = 0;
+      for (int i = 0;; ++i) {
+        const int b = i % kGwsBufs;
+        sm100::mbar_wait(&H->empty[b], ((uint32_t)(i / kGwsBufs) & 1u) ^ 1u);      // buffer free FIRST, ticket second
+        const int item = ends ? total : (int)atomicAdd(&sync[0], 1u);
+        H->item[b] = item;
+        if (item >= total) {                                                       // end markers, no data: one per apply group
+          sm100::mbar_arrive(&H->full[b]);
+          if (++ends == kGwsApplyGroups) break;
+          continue;
+        }
+        const int n = item / P.slabs, slab = item - n * P.slabs;
+        const int r0 = slab * P.rows_per_slab;
+        const int nrows = min(P.hw, r0 + P.rows_per_slab) - r0;
+        T* slab1 = reinterpret_cast<T*>(bufs + (size_t)b * kGwsBufBytes);
+        T* slab2 = slab1 + (size_t)P.rows_per_slab * c1;
+        const T* g1 = reinterpret_cast<const T*>(P.x) + ((size_t)n * P.hw + r0) * c1;
+        const uint32_t b1 = (uint32_t)((size_t)nrows * c1 * sizeof(T));
+        const uint32_t b2 = c2 ? (uint32_t)((size_t)nrows * c2 * sizeof(T)) : 0u;
+        sm100::mbar_arrive_expect_tx(&H->full[b], b1 + b2);
+        // pieces of <= 16 KB: several copies in flight per slab
+        for (uint32_t o = 0; o < b1; o += 16384u)
+          bulk_g2s(reinterpret_cast<char*>(slab1) + o, reinterpret_cast<const char*>(g1) + o, min(16384u, b1 - o), &H->full[b]);
+        if (b2) {
+          const T* g2 = reinterpret_cast<const T*>(P.x2) + ((size_t)n * P.hw + r0) * c2;
+          for (uint32_t o = 0; o < b2; o += 16384u)
+            bulk_g2s(reinterpret_cast<char*>(slab2) + o, reinterpret_cast<const char*>(g2) + o, min(16384u, b2 - o), &H->full[b]);
+        }
+      }
+    }
+  } else {
+    const bool is_stats = warp <= 8;
+    const int ag = is_stats ? 0 : (warp - 9) >> 3;                           // apply group
+    const int gt = threadIdx.x - 32 - (is_stats ? 0 : (1 + ag) * kGwsGroup); // 0..255 within the group
+    const int my_row = gt / tpr, my_chunk = gt - my_row * tpr;
+    const bool active = my_row < rpb;
+    const int ch = my_chunk * E;
+    const bool from1 = ch < c1;
+    const int ld = from1 ? c1 : c2;
+    const size_t my_off = from1 ? (size_t)ch : (size_t)P.rows_per_slab * c1 + (ch - c1);
+    const int g_lo = ch / cpg;
+    const int n_lo = min(E, (g_lo + 1) * cpg - ch);       // channels of the chunk that belong to g_lo
+
+    if (is_stats) {
+      // =========================== statistics ============================================================
+      int ends = 0;
+      for (int i = 0;; ++i) {
+        const int b = i % kGwsBufs;
+        sm100::mbar_wait(&H->full[b], (uint32_t)(i / kGwsBufs) & 1u);
+        const int item = H->item[b];
+        if (item >= total) {
+          if (gt == 0) sm100::mbar_arrive(&H->stats_done[b]);
+          if (++ends == kGwsApplyGroups) break;
+          continue;
+        }
+        const int n = item / P.slabs, slab = item - n * P.slabs;
+        const int r0 = slab * P.rows_per_slab;
+        const int nrows = min(P.hw, r0 + P.rows_per_slab) - r0;
+        const T* my_slab = reinterpret_cast<const T*>(bufs + (size_t)b * kGwsBufBytes) + my_off;
+        float av[E];
+#pragma unroll
+        for (int j = 0; j < E; ++j) av[j] = 0.f;
+        if (active && P.add_nc) V16<T>::ld(reinterpret_cast<const T*>(P.add_nc) + (size_t)n * P.c + ch, av);
+        if (active) {
+          float2 sum2[E / 2], sq2[E / 2];
+#pragma unroll
+          for (int j = 0; j < E / 2; ++j) { sum2[j] = make_float2(0.f, 0.f); sq2[j] = make_float2(0.f, 0.f); }
+#pragma unroll 4
+          for (int r = my_row; r < nrows; r += rpb) {
+            float2 v[E / 2];
+            P16<T>::unpack(*reinterpret_cast<const uint4*>(my_slab + (size_t)r * ld), v);
+#pragma unroll
+            for (int j = 0; j < E / 2; ++j) { sum2[j] = __fadd2_rn(sum2[j], v[j]); sq2[j] = __ffma2_rn(v[j], v[j], sq2[j]); }
+          }
+          float sum[E], sq[E];
+#pragma unroll
+          for (int j = 0; j < E / 2; ++j) {
+            sum[2 * j] = sum2[j].x; sum[2 * j + 1] = sum2[j].y;
+            sq[2 * j] = sq2[j].x; sq[2 * j + 1] = sq2[j].y;
+          }
+          if (P.add_nc) {                                 // sum(x + a) = sum(x) + N a, sum((x + a)^2) = sum(x^2) + a (2 sum(x) + N a)
+            const float cnt = (float)(my_row < nrows ? (nrows - my_row + rpb - 1) / rpb : 0);
+#pragma unroll
+            for (int j = 0; j < E; ++j) {
+              sq[j] = fmaf(av[j], fmaf(cnt, av[j], 2.0f * sum[j]), sq[j]);
+              sum[j] = fmaf(cnt, av[j], sum[j]);
+            }
+          }
+          float4 pr = make_float4(0.f, 0.f, 0.f, 0.f);    // (sum, sq) of g_lo, (sum, sq) of g_lo + 1
+#pragma unroll
+          for (int j = 0; j < E; ++j) {
+            if (j < n_lo) { pr.x += sum[j]; pr.y += sq[j]; }
+            else { pr.z += sum[j]; pr.w += sq[j]; }
+          }
+          s_pair[gt] = pr;
+        }
+        gws_bar(1);
+        // slab totals per group: eight lanes per group over (row lane, chunk) in a fixed order, then a fixed tree
+        {
+          const int grp = gt >> 3, sub = gt & 7;
+          if (grp < P.groups) {
+            const int k0 = (grp * cpg) / E, k1 = ((grp + 1) * cpg - 1) / E;       // chunks that touch the group
+            const int nk = k1 - k0 + 1;
+            float gs = 0.f, gq = 0.f;
+            for (int q = sub; q < nk * rpb; q += 8) {
+              const int rr = q / nk, k = k0 + (q - rr * nk);
+              const float4 pr = s_pair[rr * tpr + k];
+              const bool lo = (k * E) / cpg == grp;
+              gs += lo ? pr.x : pr.z;
+              gq += lo ? pr.y : pr.w;
+            }
+            const unsigned m8 = 0xffu << (lane & 24);
+#pragma unroll
+            for (int o = 4; o > 0; o >>= 1) {
+              gs += __shfl_xor_sync(m8, gs, o);
+              gq += __shfl_xor_sync(m8, gq, o);
+            }
+            if (sub == 0) __stcg(reinterpret_cast<float2*>(P.ws) + ((size_t)n * P.slabs + slab) * P.groups + grp, make_float2(gs, gq));
+          }
+        }
+        gws_bar(1);                                       // every partial of this slab written; s_pair free again
+        if (gt == 0) {
+          // release: the slab's partials (ordered before this thread by the barrier) become visible with the arrival
+          unsigned seen;
+          asm volatile("atom.add.release.gpu.global.u32 %0, [%1], 1;" : "=r"(seen) : "l"(&sync[2 + 2 * n]) : "memory");
+          (void)seen;
+          sm100::mbar_arrive(&H->stats_done[b]);
+        }
+      }
+    } else {
+      // =========================== apply ====================================================================
+      float gam[E], bet[E];                               // the same for every item
+#pragma unroll
+      for (int j = 0; j < E; ++j) { gam[j] = 0.f; bet[j] = 0.f; }
+      if (active) {
+        V16<T>::ld(reinterpret_cast<const T*>(P.gamma) + ch, gam);
+        V16<T>::ld(reinterpret_cast<const T*>(P.beta) + ch, bet);
+      }
+      const bool bulk_out = (set & 0x200) && c2 == 0;
+      for (int i = ag;; i += kGwsApplyGroups) {
+        const int b = i % kGwsBufs;
+        sm100::mbar_wait(&H->stats_done[b], (uint32_t)(i / kGwsBufs) & 1u);
+        const int item = H->item[b];
+        if (item >= total) break;
+        const int n = item / P.slabs, slab = item - n * P.slabs;
+        const int r0 = slab * P.rows_per_slab;
+        const int nrows = min(P.hw, r0 + P.rows_per_slab) - r0;
+        const T* my_slab = reinterpret_cast<const T*>(bufs + (size_t)b * kGwsBufBytes) + my_off;
+        float av[E];                                        // issued before the wait: needs only the sample index
+#pragma unroll
+        for (int j = 0; j < E; ++j) av[j] = 0.f;
+        if (active && P.add_nc) V16<T>::ld(reinterpret_cast<const T*>(P.add_nc) + (size_t)n * P.c + ch, av);
+        if (gt == 0) {
+          if (!(set & 0x100))                               // 0x100: VF_GN_DEBUG_NOWAIT (timing experiment, wrong results)
+            while (ld_acquire_u32(&sync[2 + 2 * n]) < (unsigned)P.slabs) __nanosleep(32);
+          asm volatile("fence.acq_rel.gpu;" ::: "memory");
+        }
+        gws_bar(2 + ag);
+        // totals of the sample: eight lanes per group, a lane's slabs (s = sub, sub + 8, ...) all in flight at once (one L2 round
+        // trip), summed in that order, then a fixed tree in double -- the same order in every CTA of the sample
+        {
+          const int grp = gt >> 3, sub = gt & 7;
+          if (grp < P.groups) {
+            const float2* w = reinterpret_cast<const float2*>(P.ws) + ((size_t)n * P.slabs) * P.groups + grp;
+            float2 v[kGwsSlabStride / 8];
+#pragma unroll
+            for (int u = 0; u < kGwsSlabStride / 8; ++u) {
+              const int sl = sub + 8 * u;
+              v[u] = sl < P.slabs ? __ldcg(w + (size_t)sl * P.groups) : make_float2(0.f, 0.f);
+            }
+            double sd = 0.0, qd = 0.0;
+#pragma unroll
+            for (int u = 0; u < kGwsSlabStride / 8; ++u) { sd += (double)v[u].x; qd += (double)v[u].y; }
+            const unsigned m8 = 0xffu << (lane & 24);
+#pragma unroll
+            for (int o = 4; o > 0; o >>= 1) {
+              sd += __shfl_xor_sync(m8, sd, o);
+              qd += __shfl_xor_sync(m8, qd, o);
+            }
+            if (sub == 0) {
+              const double cnt = (double)P.hw * cpg;
+              const double mean = sd / cnt;
+              double var = qd / cnt - mean * mean;
+              if (var < 0.0) var = 0.0;
+              H->mr[ag][grp] = make_float2((float)mean, (float)(1.0 / sqrt(var + (double)P.eps)));
+            }
+          }
+        }
+        gws_bar(2 + ag);
+        if (active) {
+          const float2 t_lo = H->mr[ag][g_lo];
+          const float2 t_hi = n_lo < E ? H->mr[ag][g_lo + 1] : t_lo;
+          // bf16 SiLU = h + h tanh(h), h = t / 2: the 1/2 is folded into scale / shift, the rest is two packed FMAs per pair
+          const float ks = P.silu ? 0.5f : 1.0f;
+          float scale[E], shift[E];
+#pragma unroll
+          for (int j = 0; j < E; ++j) {
+            const float2 t = j < n_lo ? t_lo : t_hi;
+            scale[j] = t.y * gam[j];
+            shift[j] = fmaf(av[j] - t.x, scale[j], bet[j]) * ks;
+            scale[j] *= ks;
+          }
+          float2 scale2[E / 2], shift2[E / 2];
+#pragma unroll
+          for (int j = 0; j < E / 2; ++j) {
+            scale2[j] = make_float2(scale[2 * j], scale[2 * j + 1]);
+            shift2[j] = make_float2(shift[2 * j], shift[2 * j + 1]);
+          }
+          char* q = reinterpret_cast<char*>(reinterpret_cast<T*>(P.y) + ((size_t)n * P.hw + r0 + my_row) * P.c + ch);
+          const size_t qstride = (size_t)rpb * P.c * sizeof(T);
+#pragma unroll 4
+          for (int r = my_row; r < nrows; r += rpb, q += qstride) {
+            float2 v[E / 2];
+            P16<T>::unpack(*reinterpret_cast<const uint4*>(my_slab + (size_t)r * ld), v);
+#pragma unroll
+            for (int j = 0; j < E / 2; ++j) {
+              float2 t = __ffma2_rn(v[j], scale2[j], shift2[j]);
+              if (P.silu) {
+                float2 th;
+                asm("tanh.approx.f32 %0, %1;" : "=f"(th.x) : "f"(t.x));
+                asm("tanh.approx.f32 %0, %1;" : "=f"(th.y) : "f"(t.y));
+                t = __ffma2_rn(t, th, t);
+              }
+              v[j] = t;
+            }
+            if (bulk_out) *reinterpret_cast<uint4*>(const_cast<T*>(my_slab) + (size_t)r * ld) = P16<T>::pack(v);     // in place
+            else st_na_v4(q, P16<T>::pack(v));
+          }
+          if (bulk_out) sm100::fence_proxy_async();       // generic-proxy writes -> visible to the bulk store
+        }
+        gws_bar(2 + ag);                                  // every thread is done with the buffer
+        if (gt == 0) {
+          if (bulk_out) {
+            // one source: the normalised slab is contiguous in y -- it leaves as bulk stores (the TMA engine's writes instead
+            // of 16-byte stores from every thread); the buffer goes back once they have READ it
+            const char* src = reinterpret_cast<const char*>(bufs + (size_t)b * kGwsBufBytes);
+            char* dst = reinterpret_cast<char*>(reinterpret_cast<T*>(P.y) + ((size_t)n * P.hw + r0) * P.c);
+            const uint32_t bytes = (uint32_t)((size_t)nrows * P.c * sizeof(T));
+            for (uint32_t o = 0; o < bytes; o += 16384u)
+              asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                           :: "l"(dst + o), "r"(sm100::smem_u32(src + o)), "r"(min(16384u, bytes - o)) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          }
+          sm100::mbar_arrive(&H->empty[b]);
+        }
+      }
+    }
+  }
+  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");       // bulk stores of this thread (if any) complete before exit
+  // the last CTA out re-arms the set (ticket, exit count, arrival counters and ready flags of all samples)
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    H->item[0] = (int)atomicAdd(&sync[1], 1u);
+  }
+  __syncthreads();
+  if (H->item[0] == (int)gridDim.x - 1) {
+    for (int i = threadIdx.x; i < P.n; i += blockDim.x) { sync[2 + 2 * i] = 0u; sync[3 + 2 * i] = 0u; }
+    if (threadIdx.x == 0) { sync[0] = 0u; sync[1] = 0u; }
+  }
+}
+
+static int gn_ws_launch(GnParams& P, int tpr, int rpb, cudaStream_t st) {
+  static unsigned launch_no3 = 0;
+  const int set = (int)(launch_no3++ % kGnSyncSets);
+  const size_t smem = 1024 + kGwsGroup * sizeof(float4) + kGwsBufs * kGwsBufBytes;
+  static bool attr = false;
+  if (!attr) {
+    VF_CUDA_TRY(cudaFuncSetAttribute(gn_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = true;
+  }
+  long long grid = (long long)P.n * P.slabs;
+  if (grid > num_sms()) grid = num_sms();
+  static int nowait = -1;
+  if (nowait < 0) { const char* e_ = getenv("VF_GN_DEBUG_NOWAIT"); nowait = e_ ? atoi(e_) : 0; }
+  static int ws_mode = -1;           // VF_GN_WS=2: single-source slabs leave as bulk stores out of shared memory
+  if (ws_mode < 0) { const char* e_ = getenv("VF_GN_WS"); ws_mode = e_ ? atoi(e_) : 0; }
+  gn_ws_kernel<<<(int)grid, kGwsThreads, smem, st>>>(P, tpr, rpb, set | (nowait ? 0x100 : 0) | (ws_mode >= 2 ? 0x200 : 0));
+  return check_cuda(cudaGetLastError(), "gn_ws_kernel launch");
+}
+
 // ================================================================================================
 // residual add + bias + LayerNorm (one warp per row)
 // ================================================================================================
@@ -1793,7 +2135,7 @@ extern "C" long long vf_group_norm_workspace_floats(int n, int hw, int groups) {
   if (n <= 0 || hw <= 0 || groups <= 0) return 0;
   vf::gn_plan(n, hw, &slabs, &rps);
   (void)slabs;
-  return (long long)n * 128 * groups * 2;     // 128 = the most slabs any of the slab plans hands out
+  return (long long)n * 129 * groups * 2;     // 128 = the most slabs any of the slab plans hands out; + per-sample totals (gn_ws_kernel)
 }
 
 extern "C" int vf_group_norm_nhwc(const void* x, const void* add_nc, const void* gamma, const void* beta, void* y,
@@ -1847,6 +2189,16 @@ extern "C" int vf_group_norm_nhwc_cat(const void* x, int c1, const void* x2, int
         const int rpb_r = mt / tpr;
         const int threads_r = (tpr * rpb_r + 31) / 32 * 32;
         const size_t budget = gnr_smem_per_cta() - kGnrHeaderBytes - kGnrMaxThreads * sizeof(float4);
+        // VF_GN_WS=1: the warp-specialised form (gn_ws_kernel; bf16, rows of at most 256 16-byte chunks, enough items to give
+        // every SM two)
+        static int ws_knob = -1;
+        if (ws_knob < 0) { const char* e_ = getenv("VF_GN_WS"); ws_knob = e_ ? atoi(e_) : 0; }
+        if (ws_knob && dtype == VF_BF16 && tpr <= kGwsGroup) {
+          const int rpb_w = kGwsGroup / tpr;
+          gnr_plan(n, hw, c, 2, rpb_w, kGwsBufBytes, &P.slabs, &P.rows_per_slab);
+          if (P.slabs > 0 && P.slabs <= kGwsSlabStride && (long long)n * P.slabs >= 2LL * num_sms())
+            return gn_ws_launch(P, tpr, rpb_w, st);
+        }
         // VF_GN_PIPE=1 (opt-in): two half-size slabs per CTA, the front half of the next item ahead of the wait of the
         // current one (gn_resident2_kernel).  Correct, and SLOWER (0.180 vs 0.133 ms at 96 x 4096 x 320; the same with the
         // wait skipped): what an item costs is its fixed chain of block barriers, reductions and L2 round trips, and half-size
