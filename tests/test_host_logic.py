@@ -303,3 +303,27 @@ def test_arming_norm1_does_not_register_a_submodule():
     object.__setattr__(blk.attn1, "_pre_ln", blk.norm1)
     assert list(blk.state_dict().keys()) == keys and "_pre_ln" not in dict(blk.attn1.named_modules())
     object.__setattr__(blk.attn1, "_pre_ln", None)
+
+
+def test_bench_secondary_roofline_rows_and_write_floor():
+    """bench.summarize_secondary: bytes rows against the copy peak, flop rows against the sustained tensor peak, and for the
+    projection kernel the second fraction against max(all bytes at the copy peak, written bytes at the WRITE ceiling)."""
+    import bench
+    pk = dict(hbm=6500.0, tc=1600.0, tc_sustained=1400.0, src="test")
+    ev = {
+        "linear_proj k=320 n=960+ln": [(0.25, 1.0e9, "B"), (0.25, 1.0e9, "B")],        # 1 GB in 0.25 ms, 3/4 of it written
+        "linear_proj k=320 n=320+res": [(0.15, 0.75e9, "B")],
+        "layer_norm c=320": [(0.1, 0.5e9, "B")],
+        "linear_geglu k=320 n=1280": [(0.5, 0.64e12, "flop")],
+    }
+    out = bench.summarize_secondary(ev, 2, pk, write_gbs=3840.0)
+    rows = {r["kernel"]: r for r in out["kernels"]}
+    q = rows["linear_proj k=320 n=960+ln"]
+    assert abs(q["achieved"] - 4000.0) < 1e-6 and abs(q["frac"] - 4000.0 / 6500.0) < 1e-9 and q["launches_per_step"] == 1.0
+    floor_ms = max(2.0e9 / 6500.0, 2.0e9 * 0.75 / 3840.0) / 1e9 * 1e3          # the write term wins: 0.39 ms for both launches
+    assert abs(q["frac_of_floor"] - floor_ms / 0.5) < 1e-9 and q["frac_of_floor"] > q["frac"]
+    r = rows["linear_proj k=320 n=320+res"]                                     # 1/3 written: the copy-peak term wins
+    assert abs(r["frac_of_floor"] - r["frac"]) < 1e-9
+    assert "frac_of_floor" not in rows["layer_norm c=320"]
+    g = rows["linear_geglu k=320 n=1280"]
+    assert g["bound"] == "tensor" and abs(g["achieved"] - 1280.0) < 1e-6 and abs(g["frac"] - 1280.0 / 1400.0) < 1e-9
