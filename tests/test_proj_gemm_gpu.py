@@ -94,10 +94,26 @@ def test_linear_proj_ragged_rows_and_untouched_tail():
 
 
 def test_linear_proj_refuses_ln_with_residual():
-    from vface_b200 import ops
+    from vface_b200 import ops, _lib
     x, w, r = _mk((256, 320), 1), _mk((320, 320), 2), _mk((256, 320), 3)
     with pytest.raises((RuntimeError, ValueError)):
         ops.linear_proj(x, w, None, r, ln=_ln(320, 4))
+    # and the C-ABI itself is loud about shapes and operands it does not take
+    lib = _lib.load()
+    out = torch.empty(256, 320, dtype=torch.bfloat16, device=_dev())
+    b32 = torch.zeros(2, 320, device=_dev())
+    st = torch.cuda.current_stream().cuda_stream
+    call = lambda **kw: lib.vf_linear_proj(x.data_ptr(), w.data_ptr(), kw.get("bias"), kw.get("rpb", 0), kw.get("res"), kw.get("cs"), 1e-5,
+                                           None, 0, None, out.data_ptr(), kw.get("rows", 256), kw.get("k", 320), kw.get("n", 320),
+                                           320, 320, 320, kw.get("dtype", _lib.VF_BF16), st)
+    assert call() == 0
+    assert call(k=300) != 0 and b"bad shape" in lib.vf_last_error()
+    assert call(n=200) != 0
+    assert call(dtype=_lib.VF_F32) != 0
+    assert call(bias=b32.data_ptr(), rpb=100) != 0            # not a multiple of the 128-row tile
+    assert call(bias=b32.data_ptr(), rpb=384) != 0            # does not divide the row count
+    assert call(res=out.data_ptr()) != 0                      # out aliases residual
+    torch.cuda.synchronize()
 
 
 def test_linear_proj_residual_is_added_exactly():

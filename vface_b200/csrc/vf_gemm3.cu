@@ -466,8 +466,8 @@ extern "C" int vf_linear_proj(const void* x, const void* w, const float* bias, l
                 kP3BK, kP3MaxKBlocks * kP3BK, kP3BN);
   if (ld_x < k || ld_x % 8 || ld_out < n || ld_out % 8 || (residual && (ld_res < n || ld_res % 8)))
     return fail("vf_linear_proj: bad row stride (ld_x %lld, ld_res %lld, ld_out %lld; multiples of 8 elements)", ld_x, ld_res, ld_out);
-  if (rows_per_bias < 0 || (rows_per_bias > 0 && (!bias || rows_per_bias % kP3BM)))
-    return fail("vf_linear_proj: rows_per_bias %lld must be a multiple of %d (and needs a bias)", rows_per_bias, kP3BM);
+  if (rows_per_bias < 0 || (rows_per_bias > 0 && (!bias || rows_per_bias % kP3BM || rows % rows_per_bias)))
+    return fail("vf_linear_proj: rows_per_bias %lld must be a multiple of %d that divides rows (and needs a bias)", rows_per_bias, kP3BM);
   if (out == residual || out == x) return fail("vf_linear_proj: out must not alias x or residual");
   if (ln_stats_in && (!ln_colsum || ln_stats_parts < 1 || ln_stats_parts > 16))
     return fail("vf_linear_proj: ln_stats_in needs the LayerNorm form and 1..16 partials per row (got %d)", ln_stats_parts);
